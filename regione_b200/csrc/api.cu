@@ -1,0 +1,502 @@
+// C ABI (include/regione_b200.h): kernel-level entry points and the engine that runs one patched transformer
+// forward (RegionE/FluxKontext/inplace.py:413-576 with the attention processor of :694-824) per call.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/regione_b200.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+using namespace rge;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define RGE_CUDA(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(RGE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));     \
+  } while (0)
+#define RGE_LAUNCH(expr)                                                                           \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(RGE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+  } while (0)
+
+int device_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+GemmArgs to_args(const rge_gemm_desc* d) {
+  GemmArgs a;
+  a.A = (const bf16*)d->A; a.lda = d->lda;
+  a.W = (const bf16*)d->W; a.ldw = d->ldw;
+  a.M = d->M; a.N = d->N; a.K = d->K;
+  a.bias = (const bf16*)d->bias;
+  a.epilogue = d->epilogue;
+  a.out = (bf16*)d->out; a.ldo = d->ldo;
+  a.row_map = d->row_map; a.row_off = d->row_off; a.col_off = d->col_off;
+  a.gate = (const bf16*)d->gate; a.res = (const bf16*)d->res; a.ldr = d->ldr;
+  a.norm_w = (const bf16*)d->norm_w; a.rope_cs = (const float2*)d->rope_cs;
+  a.rope_map = d->rope_map; a.rope_off = d->rope_off;
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rge_abi_version(void) { return RGE_ABI_VERSION; }
+const char* rge_last_error(void) { return g_err; }
+int64_t rge_launch_count(void) { return g_launches.load(); }
+
+int rge_op_gemm(const rge_gemm_desc* d, void* stream) {
+  if (!d || !d->A || !d->W || !d->out) return fail(RGE_ERR_INVALID, "rge_op_gemm: null operand");
+  if (d->epilogue < 0 || d->epilogue > 3) return fail(RGE_ERR_INVALID, "rge_op_gemm: bad epilogue %d", d->epilogue);
+  if (d->epilogue == RGE_EPI_NORM_ROPE && (!d->norm_w || !d->rope_cs))
+    return fail(RGE_ERR_INVALID, "rge_op_gemm: NORM_ROPE needs norm_w and rope_cs");
+  RGE_LAUNCH(launch_gemm(to_args(d), device_sms(), (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_op_attention(const rge_attn_desc* d, void* stream) {
+  if (!d || !d->Q || !d->K || !d->V || !d->O) return fail(RGE_ERR_INVALID, "rge_op_attention: null operand");
+  AttnArgs a;
+  a.Q = (const bf16*)d->Q; a.ldq = d->ldq;
+  a.K = (const bf16*)d->K; a.ldk = d->ldk;
+  a.V = (const bf16*)d->V; a.ldv = d->ldv;
+  a.O = (bf16*)d->O; a.ldo = d->ldo;
+  a.Sq = d->Sq; a.Skv = d->Skv; a.H = d->H;
+  a.scale = d->scale;
+  RGE_LAUNCH(launch_attention(a, (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_op_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, void* out, int64_t ldo,
+                       int32_t M, int32_t D, void* stream) {
+  if (!x || !scale || !shift || !out) return fail(RGE_ERR_INVALID, "rge_op_ln_modulate: null operand");
+  RGE_LAUNCH(launch_ln_modulate((const bf16*)x, ldx, (const bf16*)scale, (const bf16*)shift, (bf16*)out, ldo, M, D,
+                                (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_op_rope_table(const float* ids, float* cs, int32_t S, void* stream) {
+  if (!ids || !cs) return fail(RGE_ERR_INVALID, "rge_op_rope_table: null operand");
+  RGE_LAUNCH(launch_rope_table(ids, (float2*)cs, S, (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_gather_rows(const void* src, int64_t lds, const int32_t* ids, int32_t n, int32_t width, void* dst,
+                    int64_t ldd, void* stream) {
+  if (n > 0 && (!src || !ids || !dst)) return fail(RGE_ERR_INVALID, "rge_gather_rows: null operand");
+  RGE_LAUNCH(launch_gather_rows((const bf16*)src, lds, ids, n, width, (bf16*)dst, ldd, (cudaStream_t)stream));
+  return RGE_OK;
+}
+int rge_scatter_rows(const void* src, int64_t lds, const int32_t* ids, int32_t n, int32_t width, void* dst,
+                     int64_t ldd, void* stream) {
+  if (n > 0 && (!src || !ids || !dst)) return fail(RGE_ERR_INVALID, "rge_scatter_rows: null operand");
+  RGE_LAUNCH(launch_scatter_rows((const bf16*)src, lds, ids, n, width, (bf16*)dst, ldd, (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_euler(const void* x, const void* v, void* out, int32_t M, int32_t channels, float dt, float dt_direct,
+              const uint8_t* edited_mask, int32_t reuse_on, float ratio, void* stream) {
+  if (M > 0 && (!x || !v || !out)) return fail(RGE_ERR_INVALID, "rge_euler: null operand");
+  RGE_LAUNCH(launch_euler((const bf16*)x, (const bf16*)v, (bf16*)out, M, channels, dt, dt_direct, edited_mask,
+                          reuse_on, ratio, (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_partition(const void* x, const void* v, const void* cond, float dt_final, float threshold,
+                  uint8_t* mask_out, float* sim_out, int32_t L, int32_t channels, void* stream) {
+  if (!x || !v || !cond || !mask_out) return fail(RGE_ERR_INVALID, "rge_partition: null operand");
+  RGE_LAUNCH(launch_arp_similarity((const bf16*)x, (const bf16*)v, (const bf16*)cond, dt_final, threshold, mask_out,
+                                   sim_out, L, channels, (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_compact(const uint8_t* mask_in, uint8_t* mask_out, int32_t grid_h, int32_t grid_w, int32_t erosion_dilation,
+                int32_t* edited_ids, int32_t* unedited_ids, int32_t* counts, void* stream) {
+  if (!mask_in || !edited_ids || !unedited_ids || !counts) return fail(RGE_ERR_INVALID, "rge_compact: null operand");
+  RGE_LAUNCH(launch_morph_compact(mask_in, mask_out, grid_h, grid_w, erosion_dilation, edited_ids, unedited_ids,
+                                  counts, (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+}  // extern "C"
+
+// ====================================================================================================== engine
+struct rge_handle {
+  rge_config cfg;
+  int T, L, C, S, D, H, Dm, n_layers, num_sms;
+  std::vector<const void*> gw, dw, sw;
+  bool finalized = false;
+  std::vector<char> begun;
+  // workspaces
+  bf16 *h = nullptr, *n = nullptr, *q = nullptr, *big = nullptr;
+  bf16 *kcache = nullptr, *vcache = nullptr;
+  bf16 *mods = nullptr, *small = nullptr;  // small: tproj[256] t1[D] t2[D] temb[D]
+  bf16 *ctx = nullptr;                     // [n_pass][T, D]
+  bf16 *pass_small = nullptr;              // per pass: gproj[256] g1[D] gemb[D] pooled[pooled_dim] p1[D] pemb[D]
+  float2* rope = nullptr;                  // [n_pass][S, 64]
+  float* ids = nullptr;                    // [S, 3] staging
+  int *sel_img = nullptr, *sel_all = nullptr;
+  GemvJob* jobs = nullptr;                 // [2 + n_mod] step jobs, then per pass 4 image jobs
+  int n_mod = 0;
+  size_t pass_small_stride = 0;
+
+  const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
+  const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
+  const bf16* Sw(int b, int slot) const { return (const bf16*)sw[(size_t)b * RGE_S_NUM_SLOTS + slot]; }
+  bf16* kc(int pass, int layer) const { return kcache + ((size_t)pass * n_layers + layer) * (size_t)S * D; }
+  bf16* vc(int pass, int layer) const { return vcache + ((size_t)pass * n_layers + layer) * (size_t)S * D; }
+  bf16* ps(int pass) const { return pass_small + (size_t)pass * pass_small_stride; }
+};
+
+namespace {
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+  return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bias, int N,
+         int epi, bf16* out, long ldo, const int* row_map, int row_off, int col_off, const bf16* gate = nullptr,
+         const bf16* res = nullptr, long ldr = 0, const bf16* norm_w = nullptr, const float2* rope = nullptr,
+         const int* rope_map = nullptr, int rope_off = 0) {
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.M = M; a.K = K; a.W = W; a.ldw = K; a.N = N; a.bias = bias; a.epilogue = epi;
+  a.out = out; a.ldo = ldo; a.row_map = row_map; a.row_off = row_off; a.col_off = col_off;
+  a.gate = gate; a.res = res; a.ldr = ldr; a.norm_w = norm_w; a.rope_cs = rope; a.rope_map = rope_map;
+  a.rope_off = rope_off;
+  if (M <= 0) return RGE_OK;
+  RGE_LAUNCH(launch_gemm(a, h->num_sms, st));
+  return RGE_OK;
+}
+
+#define RGE_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != RGE_OK) return _r; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int rge_create(const rge_config* cfg, rge_handle** out) {
+  if (!cfg || !out) return fail(RGE_ERR_INVALID, "rge_create: null argument");
+  if (cfg->dim <= 0 || cfg->heads <= 0 || cfg->dim != cfg->heads * 128)
+    return fail(RGE_ERR_UNSUPPORTED, "rge_create: head_dim must be 128 (dim %d heads %d)", cfg->dim, cfg->heads);
+  if (cfg->dim > 4096 || cfg->pooled_dim > 4096 || cfg->dim % 256)
+    return fail(RGE_ERR_UNSUPPORTED, "rge_create: dim must be a multiple of 256 and <= 4096");
+  if (cfg->in_channels % 32 || cfg->ctx_dim % 8 || cfg->pooled_dim % 8 || cfg->txt_len < 0 || cfg->lat_len <= 0 ||
+      cfg->cond_len < 0 || cfg->n_pass < 1 || cfg->mlp_ratio < 1 || cfg->n_double < 0 || cfg->n_single < 0)
+    return fail(RGE_ERR_INVALID, "rge_create: bad shape");
+  RGE_CUDA(cudaSetDevice(cfg->device));
+  if (!get_tensor_map_encoder()) return fail(RGE_ERR_CUDA, "rge_create: cuTensorMapEncodeTiled not available");
+  rge_handle* h = new (std::nothrow) rge_handle();
+  if (!h) return fail(RGE_ERR_INVALID, "rge_create: out of host memory");
+  h->cfg = *cfg;
+  h->T = cfg->txt_len; h->L = cfg->lat_len; h->C = cfg->cond_len; h->S = h->T + h->L + h->C;
+  h->D = cfg->dim; h->H = cfg->heads; h->Dm = cfg->dim * cfg->mlp_ratio;
+  h->n_layers = cfg->n_double + cfg->n_single;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  h->gw.assign(RGE_G_NUM_SLOTS, nullptr);
+  h->dw.assign((size_t)cfg->n_double * RGE_D_NUM_SLOTS, nullptr);
+  h->sw.assign((size_t)cfg->n_single * RGE_S_NUM_SLOTS, nullptr);
+  h->begun.assign(cfg->n_pass, 0);
+  const size_t S = h->S, D = h->D;
+  h->n_mod = cfg->n_double * 2 + cfg->n_single + 1;
+  const size_t mods_elems = (size_t)cfg->n_double * 12 * D + (size_t)cfg->n_single * 3 * D + 2 * D;
+  h->pass_small_stride = 256 + 5 * D + cfg->pooled_dim + 64;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(dalloc(&h->h, S * D));
+  A(dalloc(&h->n, S * D));
+  A(dalloc(&h->q, S * D));
+  A(dalloc(&h->big, S * (D + (size_t)h->Dm)));
+  A(dalloc(&h->kcache, (size_t)cfg->n_pass * h->n_layers * S * D));
+  A(dalloc(&h->vcache, (size_t)cfg->n_pass * h->n_layers * S * D));
+  A(dalloc(&h->mods, mods_elems));
+  A(dalloc(&h->small, 256 + 3 * D));
+  A(dalloc(&h->ctx, (size_t)cfg->n_pass * h->T * D + 8));
+  A(dalloc(&h->pass_small, (size_t)cfg->n_pass * h->pass_small_stride));
+  A(dalloc(&h->rope, (size_t)cfg->n_pass * S * 64));
+  A(dalloc(&h->ids, S * 3));
+  A(dalloc(&h->sel_img, S));
+  A(dalloc(&h->sel_all, S));
+  A(dalloc(&h->jobs, (size_t)2 + h->n_mod + 4 * cfg->n_pass));
+  if (e != cudaSuccess) {
+    rge_destroy(h);
+    return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));
+  }
+  // the cache must never expose uninitialised rows to attention
+  cudaMemset(h->kcache, 0, (size_t)cfg->n_pass * h->n_layers * S * D * sizeof(bf16));
+  cudaMemset(h->vcache, 0, (size_t)cfg->n_pass * h->n_layers * S * D * sizeof(bf16));
+  RGE_CUDA(cudaDeviceSynchronize());
+  *out = h;
+  return RGE_OK;
+}
+
+int rge_destroy(rge_handle* h) {
+  if (!h) return RGE_OK;
+  void* ptrs[] = {h->h, h->n, h->q, h->big, h->kcache, h->vcache, h->mods, h->small, h->ctx, h->pass_small,
+                  h->rope, h->ids, h->sel_img, h->sel_all, h->jobs};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete h;
+  return RGE_OK;
+}
+
+int rge_set_weight(rge_handle* h, int32_t kind, int32_t index, int32_t slot, const void* ptr) {
+  if (!h || !ptr) return fail(RGE_ERR_INVALID, "rge_set_weight: null argument");
+  if (kind == RGE_BLK_GLOBAL) {
+    if (slot < 0 || slot >= RGE_G_NUM_SLOTS) return fail(RGE_ERR_INVALID, "rge_set_weight: bad global slot %d", slot);
+    h->gw[slot] = ptr;
+  } else if (kind == RGE_BLK_DOUBLE) {
+    if (index < 0 || index >= h->cfg.n_double || slot < 0 || slot >= RGE_D_NUM_SLOTS)
+      return fail(RGE_ERR_INVALID, "rge_set_weight: bad double block %d slot %d", index, slot);
+    h->dw[(size_t)index * RGE_D_NUM_SLOTS + slot] = ptr;
+  } else if (kind == RGE_BLK_SINGLE) {
+    if (index < 0 || index >= h->cfg.n_single || slot < 0 || slot >= RGE_S_NUM_SLOTS)
+      return fail(RGE_ERR_INVALID, "rge_set_weight: bad single block %d slot %d", index, slot);
+    h->sw[(size_t)index * RGE_S_NUM_SLOTS + slot] = ptr;
+  } else {
+    return fail(RGE_ERR_INVALID, "rge_set_weight: bad block kind %d", kind);
+  }
+  h->finalized = false;
+  return RGE_OK;
+}
+
+int rge_finalize_weights(rge_handle* h) {
+  if (!h) return fail(RGE_ERR_INVALID, "rge_finalize_weights: null handle");
+  for (int s = 0; s < RGE_G_NUM_SLOTS; ++s) {
+    const bool guid = s >= RGE_G_GUID1_W && s <= RGE_G_GUID2_B;
+    if (!h->gw[s] && !(guid && !h->cfg.guidance_embeds))
+      return fail(RGE_ERR_STATE, "rge_finalize_weights: global slot %d not set", s);
+  }
+  for (size_t i = 0; i < h->dw.size(); ++i)
+    if (!h->dw[i])
+      return fail(RGE_ERR_STATE, "rge_finalize_weights: double block %d slot %d not set", (int)(i / RGE_D_NUM_SLOTS),
+                  (int)(i % RGE_D_NUM_SLOTS));
+  for (size_t i = 0; i < h->sw.size(); ++i)
+    if (!h->sw[i])
+      return fail(RGE_ERR_STATE, "rge_finalize_weights: single block %d slot %d not set", (int)(i / RGE_S_NUM_SLOTS),
+                  (int)(i % RGE_S_NUM_SLOTS));
+  const int D = h->D;
+  std::vector<GemvJob> jobs((size_t)2 + h->n_mod + 4 * h->cfg.n_pass);
+  bf16* tproj = h->small;
+  bf16* t1 = tproj + 256;
+  bf16* t2 = t1 + D;
+  bf16* temb = t2 + D;
+  // time_text_embed.timestep_embedder: Linear(256->D) + SiLU, Linear(D->D)   
+  jobs[0] = GemvJob{h->G(RGE_G_TIME1_W), h->G(RGE_G_TIME1_B), tproj, t1, D, 256, 0, 1};
+  jobs[1] = GemvJob{h->G(RGE_G_TIME2_W), h->G(RGE_G_TIME2_B), t1, t2, D, D, 0, 0};
+  // adaLN modulation of every block in one launch: Linear(silu(temb))
+  size_t j = 2;
+  bf16* m = h->mods;
+  for (int b = 0; b < h->cfg.n_double; ++b) {
+    jobs[j++] = GemvJob{h->Dw(b, RGE_D_MOD_W), h->Dw(b, RGE_D_MOD_B), temb, m, 6 * D, D, 1, 0};
+    m += 6 * D;
+    jobs[j++] = GemvJob{h->Dw(b, RGE_D_MOD_CTX_W), h->Dw(b, RGE_D_MOD_CTX_B), temb, m, 6 * D, D, 1, 0};
+    m += 6 * D;
+  }
+  for (int b = 0; b < h->cfg.n_single; ++b) {
+    jobs[j++] = GemvJob{h->Sw(b, RGE_S_MOD_W), h->Sw(b, RGE_S_MOD_B), temb, m, 3 * D, D, 1, 0};
+    m += 3 * D;
+  }
+  jobs[j++] = GemvJob{h->G(RGE_G_NORM_OUT_W), h->G(RGE_G_NORM_OUT_B), temb, m, 2 * D, D, 1, 0};
+  // per pass: guidance_embedder and text_embedder (pooled) MLPs, evaluated once per image
+  for (int p = 0; p < h->cfg.n_pass; ++p) {
+    bf16* gproj = h->ps(p);
+    bf16* g1 = gproj + 256;
+    bf16* gemb = g1 + D;
+    bf16* pooled = gemb + D;
+    bf16* p1 = pooled + h->cfg.pooled_dim;
+    bf16* pemb = p1 + D;
+    if (h->cfg.guidance_embeds) {
+      jobs[j++] = GemvJob{h->G(RGE_G_GUID1_W), h->G(RGE_G_GUID1_B), gproj, g1, D, 256, 0, 1};
+      jobs[j++] = GemvJob{h->G(RGE_G_POOL1_W), h->G(RGE_G_POOL1_B), pooled, p1, D, h->cfg.pooled_dim, 0, 1};
+      jobs[j++] = GemvJob{h->G(RGE_G_GUID2_W), h->G(RGE_G_GUID2_B), g1, gemb, D, D, 0, 0};
+      jobs[j++] = GemvJob{h->G(RGE_G_POOL2_W), h->G(RGE_G_POOL2_B), p1, pemb, D, D, 0, 0};
+    } else {
+      jobs[j++] = GemvJob{h->G(RGE_G_POOL1_W), h->G(RGE_G_POOL1_B), pooled, p1, D, h->cfg.pooled_dim, 0, 1};
+      jobs[j++] = GemvJob{h->G(RGE_G_POOL1_W), h->G(RGE_G_POOL1_B), pooled, p1, D, h->cfg.pooled_dim, 0, 1};
+      jobs[j++] = GemvJob{h->G(RGE_G_POOL2_W), h->G(RGE_G_POOL2_B), p1, pemb, D, D, 0, 0};
+      jobs[j++] = GemvJob{h->G(RGE_G_POOL2_W), h->G(RGE_G_POOL2_B), p1, pemb, D, D, 0, 0};
+    }
+  }
+  RGE_CUDA(cudaMemcpy(h->jobs, jobs.data(), jobs.size() * sizeof(GemvJob), cudaMemcpyHostToDevice));
+  h->finalized = true;
+  return RGE_OK;
+}
+
+int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const float* img_ids, const void* enc,
+                    const void* pooled, float guidance_x1000, void* stream) {
+  if (!h || !img_ids || !enc || !pooled) return fail(RGE_ERR_INVALID, "rge_begin_image: null argument");
+  if (h->T > 0 && !txt_ids) return fail(RGE_ERR_INVALID, "rge_begin_image: null txt_ids");
+  if (!h->finalized) return fail(RGE_ERR_STATE, "rge_begin_image: weights not finalized");
+  if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_begin_image: bad pass %d", pass);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = h->D, T = h->T;
+  // key-side rotary table over the FULL sequence (MANAGER.image_rotary_emb, inplace.py:499); query rows are
+  // looked up in the same table through the selection, which equals pos_embed(gathered ids) (:495-496)
+  if (T > 0) RGE_CUDA(cudaMemcpyAsync(h->ids, txt_ids, (size_t)T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RGE_CUDA(cudaMemcpyAsync(h->ids + (size_t)T * 3, img_ids, (size_t)(h->L + h->C) * 3 * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  RGE_LAUNCH(launch_rope_table(h->ids, h->rope + (size_t)pass * h->S * 64, h->S, st));
+  // context_embedder (inplace.py:480): same value every step of the image, so computed once
+  RGE_TRY(gemm(h, st, (const bf16*)enc, h->cfg.ctx_dim, T, h->cfg.ctx_dim, h->G(RGE_G_CTX_EMBED_W),
+               h->G(RGE_G_CTX_EMBED_B), D, EPI_STORE, h->ctx + (size_t)pass * T * D, D, nullptr, 0, 0));
+  // guidance / pooled halves of time_text_embed (inplace.py:475-479)
+  bf16* gproj = h->ps(pass);
+  bf16* pooled_buf = gproj + 256 + 2 * D;
+  RGE_CUDA(cudaMemcpyAsync(pooled_buf, pooled, (size_t)h->cfg.pooled_dim * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  if (h->cfg.guidance_embeds) RGE_LAUNCH(launch_timestep_proj(guidance_x1000, gproj, st));
+  const GemvJob* pj = h->jobs + 2 + h->n_mod + 4 * pass;
+  RGE_LAUNCH(launch_gemv_batch(pj, 2, D, st));
+  RGE_LAUNCH(launch_gemv_batch(pj + 2, 2, D, st));
+  h->begun[pass] = 1;
+  return RGE_OK;
+}
+
+int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
+                 float timestep_x1000, void* v_out, int32_t n_out, void* stream) {
+  if (!h || !v_out || (n_img > 0 && !x_in)) return fail(RGE_ERR_INVALID, "rge_dit_step: null argument");
+  if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_dit_step: bad pass %d", pass);
+  if (!h->finalized || !h->begun[pass]) return fail(RGE_ERR_STATE, "rge_dit_step: rge_begin_image not called");
+  if (n_img < 0 || n_img > h->L + h->C || (!sel && n_img != h->L + h->C))
+    return fail(RGE_ERR_INVALID, "rge_dit_step: n_img %d invalid (sel %s, L+C %d)", n_img, sel ? "set" : "null",
+                h->L + h->C);
+  if (n_out < 0 || n_out > n_img) return fail(RGE_ERR_INVALID, "rge_dit_step: n_out %d > n_img %d", n_out, n_img);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = h->D, T = h->T, Dm = h->Dm, S = h->S, M = n_img, MA = T + n_img;
+  const long ldb = D + Dm;  // `big`: attention output in columns [0,D), MLP hidden in [D, D+Dm)
+  const float2* rope = h->rope + (size_t)pass * S * 64;
+  bf16* tproj = h->small;
+  bf16* t2 = tproj + 256 + D;
+  bf16* temb = t2 + D;
+  const bf16* gemb = h->ps(pass) + 256 + D;
+  const bf16* pemb = h->ps(pass) + 256 + 2 * D + h->cfg.pooled_dim + D;
+
+  RGE_LAUNCH(launch_build_selection(sel, M, T, h->sel_img, h->sel_all, st));
+  // ---- temb = timestep_embedder(proj(t)) [+ guidance_embedder(..)] + text_embedder(pooled)
+  RGE_LAUNCH(launch_timestep_proj(timestep_x1000, tproj, st));
+  RGE_LAUNCH(launch_gemv_batch(h->jobs, 1, D, st));
+  RGE_LAUNCH(launch_gemv_batch(h->jobs + 1, 1, D, st));
+  if (h->cfg.guidance_embeds) RGE_LAUNCH(launch_add3(t2, gemb, pemb, temb, D, st));
+  else RGE_LAUNCH(launch_add3(t2, pemb, nullptr, temb, D, st));
+  // ---- adaLN modulation vectors of all blocks
+  RGE_LAUNCH(launch_gemv_batch(h->jobs + 2, h->n_mod, 6 * D, st));
+  // ---- token embedding: text rows [0,T) come from the per-image context embedding, image rows from x_embedder
+  if (T > 0)
+    RGE_CUDA(cudaMemcpyAsync(h->h, h->ctx + (size_t)pass * T * D, (size_t)T * D * sizeof(bf16),
+                             cudaMemcpyDeviceToDevice, st));
+  RGE_TRY(gemm(h, st, (const bf16*)x_in, h->cfg.in_channels, M, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
+               h->G(RGE_G_X_EMBED_B), D, EPI_STORE, h->h, D, nullptr, T, 0));
+
+  bf16* x_img = h->h + (size_t)T * D;
+  bf16* n_img_p = h->n + (size_t)T * D;
+  bf16* big_img = h->big + (size_t)T * ldb;
+  const bf16* mod = h->mods;
+  int layer = 0;
+  // ---- double-stream blocks
+  for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
+    const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
+               *g_mlp = mod + 5 * D;
+    const bf16* cm = mod + 6 * D;
+    const bf16 *csh_msa = cm, *csc_msa = cm + D, *cg_msa = cm + 2 * D, *csh_mlp = cm + 3 * D, *csc_mlp = cm + 4 * D,
+               *cg_mlp = cm + 5 * D;
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, st));
+    // image stream q/k/v; k,v rows scattered into the cache at T + sel[m]
+    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr,
+                 T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T));
+    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D,
+                 h->sel_img, T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T));
+    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T,
+                 0));
+    // text stream q/k/v (recomputed every step: the reference does not cache text K/V)
+    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D,
+                 nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0));
+    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D,
+                 nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0));
+    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0,
+                 0));
+    AttnArgs at;
+    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
+    at.Sq = MA; at.Skv = S; at.H = h->H;
+    RGE_LAUNCH(launch_attention(at, st));
+    // out projections with gate * (.) + residual fused
+    RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
+                 nullptr, 0, 0, g_msa, x_img, D));
+    RGE_TRY(gemm(h, st, h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h,
+                 D, nullptr, 0, 0, cg_msa, h->h, D));
+    // feed-forward, both streams
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, st));
+    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb,
+                 nullptr, 0, D));
+    RGE_TRY(gemm(h, st, big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES,
+                 x_img, D, nullptr, 0, 0, g_mlp, x_img, D));
+    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb,
+                 nullptr, 0, D));
+    RGE_TRY(gemm(h, st, h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES,
+                 h->h, D, nullptr, 0, 0, cg_mlp, h->h, D));
+  }
+  // ---- single-stream blocks on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
+  for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
+    const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
+    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
+                 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0));
+    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
+                 0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
+    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
+                 0));
+    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr,
+                 0, D));
+    AttnArgs at;
+    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
+    at.Sq = MA; at.Skv = S; at.H = h->H;
+    RGE_LAUNCH(launch_attention(at, st));
+    RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
+                 nullptr, 0, 0, g, h->h, D));
+  }
+  // ---- norm_out (scale first, then shift) + proj_out on the noise rows only (App. C-9)
+  RGE_LAUNCH(launch_ln_modulate(x_img, D, mod, mod + D, n_img_p, D, n_out, D, st));
+  RGE_TRY(gemm(h, st, n_img_p, D, n_out, D, h->G(RGE_G_PROJ_OUT_W), h->G(RGE_G_PROJ_OUT_B), h->cfg.in_channels,
+               EPI_STORE, (bf16*)v_out, h->cfg.in_channels, nullptr, 0, 0));
+  return RGE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+// tcgen05/TMEM flash attention for the RegionE hot path: active-Q x cached-KV, non-causal, head_dim 128.
+//
+// One CTA owns 256 query rows (two 128-row tiles) of one head and streams the whole K/V cache of that head:
+//   warp 0        TMA producer: Q once, then K_j / V_j tiles through a 5-slot shared-memory ring
+//   warp 1        MMA issuer (one thread): S_i = Q_i K_j^T (SS), O_i += P_i V_j (P from TMEM, V MN-major from smem)
+//   warps 2-5     softmax group 0 (query tile 0), one thread per query row
+//   warps 6-9     softmax group 1 (query tile 1)
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_i (bf16 pairs) overwrites the first 64 columns
+// of S_i once a row's scores are in registers. The two tiles ping-pong so the tensor pipe works on one while the
+// other's softmax runs. Online softmax uses a lazy reference maximum: O is only rescaled (by the softmax group
+// itself, in TMEM) when a row maximum grows by more than 2^8.
+//
+// Replaces flash_attn_func(q, k, v, causal=False) at RegionE/FluxKontext/inplace.py:796-801; K/V are read in place
+// from the Region-Instruction KV cache instead of being re-normalised, re-rotated and re-concatenated every step
+// (inplace.py:756-794).
+#include "attention.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace rge {
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kTile = 128;             // query rows per tile, kv rows per tile, head dim
+constexpr int kHalfBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled half tile
+constexpr int kTileBytes = 2 * kHalfBytes;
+constexpr int kSlots = 5;
+constexpr int kSmemBytes = 2 * kTileBytes + kSlots * kTileBytes + 256 + 1024;
+constexpr uint32_t kColS = 0, kColO = 256;  // TMEM column bases: S_i at kColS + 128 i, O_i at kColO + 128 i
+
+struct AttnDev {
+  __nv_bfloat16* O;
+  long ldo;
+  int Sq, Skv;
+  float sl2;  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_kv = smem + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + kSlots * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + kSlots;
+  uint64_t* s_full = kv_empty + kSlots;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_bar = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 2 * kTile;
+  const int n_tiles = (p.Skv + kTile - 1) / kTile;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_bar[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+      for (int i = 0; i < 2; ++i)
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d(s_q + i * kTileBytes + half * kHalfBytes, &map_q, q_full, head * 128 + half * 64,
+                      q0 + i * kTile);
+      for (int t = 0; t < 2 * n_tiles; ++t) {
+        const int slot = t % kSlots;
+        const uint32_t ph = (t / kSlots) & 1;
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
+        const CUtensorMap* map = (t & 1) ? &map_v : &map_k;
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d(s_kv + slot * kTileBytes + half * kHalfBytes, map, &kv_full[slot], head * 128 + half * 64,
+                      (t >> 1) * kTile);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+      const uint32_t sq_addr = smem_u32(s_q);
+      const uint32_t skv_addr = smem_u32(s_kv);
+      auto slot_addr = [&](int t) { return skv_addr + (t % kSlots) * kTileBytes; };
+      auto wait_kv = [&](int t) {
+        mbar_wait(&kv_full[t % kSlots], (t / kSlots) & 1);
+        tc_fence_after();
+      };
+      // S_i = Q_i K^T : contraction over d, 8 steps of 16; both operands K-major, 128B-swizzled
+      auto issue_qk = [&](int i, uint32_t k_addr) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          umma_ss(tmem + kColS + i * 128, make_sdesc_sw128(sq_addr + i * kTileBytes + off, 0, 1024),
+                  make_sdesc_sw128(k_addr + off, 0, 1024), idesc_qk, kk != 0);
+        }
+      };
+      // O_i += P_i V : contraction over kv, 8 steps of 16 rows (2048 B); V is [kv][d] = MN-major B with two
+      // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO)
+      auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8,
+                  make_sdesc_sw128(v_addr + kk * 2048, kHalfBytes, 1024), idesc_pv, accumulate || kk != 0);
+        }
+      };
+      mbar_wait(q_full, 0);
+      wait_kv(0);
+      issue_qk(0, slot_addr(0));
+      tc_commit(&s_full[0]);
+      issue_qk(1, slot_addr(0));
+      tc_commit(&s_full[1]);
+      tc_commit(&kv_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int tv = 2 * j + 1, tk = 2 * j + 2;
+        const bool more = j + 1 < n_tiles;
+        wait_kv(tv);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, slot_addr(tv), j > 0);
+        tc_commit(&o_bar[0]);
+        if (more) {
+          wait_kv(tk);
+          issue_qk(0, slot_addr(tk));
+          tc_commit(&s_full[0]);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, slot_addr(tv), j > 0);
+        tc_commit(&o_bar[1]);
+        tc_commit(&kv_empty[tv % kSlots]);
+        if (more) {
+          issue_qk(1, slot_addr(tk));
+          tc_commit(&s_full[1]);
+          tc_commit(&kv_empty[tk % kSlots]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax groups
+    const int grp = (warp - 2) >> 2;  // query tile handled by this warp group
+    const int qtr = warp & 3;         // TMEM lane quarter this warp may access
+    const int row = q0 + grp * kTile + qtr * 32 + lane;
+    const uint32_t lane_base = uint32_t(qtr * 32) << 16;
+    const uint32_t t_s = tmem + lane_base + kColS + grp * 128;
+    const uint32_t t_o = tmem + lane_base + kColO + grp * 128;
+    const float sl2 = p.sl2;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[grp], j & 1);
+      tc_fence_after();
+      const int n_valid = min(kTile, p.Skv - j * kTile);
+      // pass 1: row maximum of the raw scores
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          float s = __uint_as_float(v[jj]);
+          if (c * 32 + jj < n_valid) mx = fmaxf(mx, s);
+        }
+      }
+      if (j == 0) {
+        m_run = mx;
+      } else {
+        const bool need = (mx - m_run) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // O_i must be quiescent: PV_i(j-1) complete, PV_i(j) not issued before our p_full arrive
+          mbar_wait(&o_bar[grp], (j - 1) & 1);
+          tc_fence_after();
+          const float m_new = need ? mx : m_run;
+          const float alpha = ex2((m_run - m_new) * sl2);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_o + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) * alpha);
+            tmem_st32(t_o + c * 32, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_run = m_new;
+        }
+      }
+      // pass 2: P = exp2((s - m) * scale * log2 e), packed bf16 pairs into the first 64 columns of S_i
+      const float neg_m = -m_run * sl2;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(v[jj]), sl2, neg_m));
+          float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
+          if (c * 32 + jj >= n_valid) p0 = 0.f;
+          if (c * 32 + jj + 1 >= n_valid) p1 = 0.f;
+          l_run += p0 + p1;
+          pk[jj >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+    }
+    // epilogue: O_i / l -> bf16 -> global
+    mbar_wait(&o_bar[grp], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const bool valid = row < p.Sq;
+    __nv_bfloat16* orow = p.O + (long)(valid ? row : 0) * p.ldo + head * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_o + c * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * t + 0]) * inv, __uint_as_float(v[8 * t + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[8 * t + 2]) * inv, __uint_as_float(v[8 * t + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[8 * t + 4]) * inv, __uint_as_float(v[8 * t + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[8 * t + 6]) * inv, __uint_as_float(v[8 * t + 7]) * inv);
+          dst[t] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
+  if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap mq, mk, mv;
+  if (!make_tmap_bf16_2d(&mq, a.Q, a.Sq, (uint64_t)a.H * 128, a.ldq, kTile)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&mk, a.K, a.Skv, (uint64_t)a.H * 128, a.ldk, kTile)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&mv, a.V, a.Skv, (uint64_t)a.H * 128, a.ldv, kTile)) return cudaErrorInvalidValue;
+  AttnDev p;
+  p.O = a.O;
+  p.ldo = a.ldo;
+  p.Sq = a.Sq;
+  p.Skv = a.Skv;
+  p.sl2 = a.scale * 1.4426950408889634f;
+  dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
+  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  return cudaGetLastError();
+}
+
+}  // namespace rge

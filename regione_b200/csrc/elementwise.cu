@@ -1,0 +1,403 @@
+// HBM-bound kernels: LayerNorm+adaLN modulation, batched GEMV (adaLN / time-text embedding), rotary table,
+// row gather/scatter, Euler / velocity-decay reuse, adaptive region partition, morphology + compaction.
+// Reference behaviour restated per kernel; see oracle/ for the CPU restatement the tests compare against.
+#include "elementwise.cuh"
+#include "ptx.cuh"
+
+namespace rge {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------ LayerNorm + modulation
+// diffusers AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous body:
+//   x = LayerNorm(x, eps=1e-6, no affine) * (1 + scale) + shift     (all bf16 tensors, fp32 statistics)
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
+                                                          const __nv_bfloat16* __restrict__ scale,
+                                                          const __nv_bfloat16* __restrict__ shift,
+                                                          __nv_bfloat16* __restrict__ out, long ldo, int M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long)m * ldx);
+  const int nv = D >> 3;
+  float s = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(xr[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(xr[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = f[j] - mean;
+      q += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale);
+  const uint4* sh = reinterpret_cast<const uint4*>(shift);
+  uint4* o = reinterpret_cast<uint4*>(out + (long)m * ldo);
+  for (int i = lane; i < nv; i += 32) {
+    float f[8], a[8], b[8];
+    unpack8(xr[i], f);
+    unpack8(__ldg(sc + i), a);
+    unpack8(__ldg(sh + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float n = bf16_round((f[j] - mean) * rstd);
+      float t = bf16_round(n * bf16_round(1.0f + a[j]));
+      f[j] = t + b[j];
+    }
+    o[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------ batched GEMV
+__global__ void __launch_bounds__(256) gemv_batch_kernel(const GemvJob* __restrict__ jobs) {
+  extern __shared__ float xs[];
+  const GemvJob job = jobs[blockIdx.y];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x * 8 >= job.N) return;
+  for (int k = threadIdx.x; k < job.K; k += blockDim.x) {
+    float v = __bfloat162float(job.x[k]);
+    if (job.silu_in) v = bf16_round(silu_f(v));
+    xs[k] = v;
+  }
+  __syncthreads();
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= job.N) return;
+  const uint4* wr = reinterpret_cast<const uint4*>(job.W + (long)n * job.K);
+  const int nv = job.K >> 3;
+  float acc = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(__ldg(wr + i), f);
+    const float* xv = xs + i * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(f[j], xv[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float y = bf16_round(acc + (job.b ? __bfloat162float(job.b[n]) : 0.f));
+    if (job.silu_out) y = silu_f(y);
+    job.out[n] = __float2bfloat16_rn(y);
+  }
+}
+
+// ------------------------------------------------------------------ timestep projection / small adds
+__global__ void timestep_proj_kernel(float t, __nv_bfloat16* out) {
+  const int i = threadIdx.x;  // 0..127
+  const float exponent = (-9.210340371976184f * (float)i) / 128.0f;  // -ln(10000) * i / half_dim
+  const float arg = t * expf(exponent);
+  out[i] = __float2bfloat16_rn(cosf(arg));
+  out[128 + i] = __float2bfloat16_rn(sinf(arg));
+}
+__global__ void add3_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c,
+                            __nv_bfloat16* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = bf16_round(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+  if (c) s = s + __bfloat162float(c[i]);
+  out[i] = __float2bfloat16_rn(s);
+}
+
+// ------------------------------------------------------------------ rotary table (FluxPosEmbed)
+__global__ void rope_table_kernel(const float* __restrict__ ids, float2* __restrict__ cs, int S) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * 64) return;
+  const int s = idx >> 6, p = idx & 63;
+  int axis, j, dim;
+  if (p < 8) { axis = 0; j = p; dim = 16; }
+  else if (p < 36) { axis = 1; j = p - 8; dim = 56; }
+  else { axis = 2; j = p - 36; dim = 56; }
+  const double freq = 1.0 / pow(10000.0, (double)(2 * j) / (double)dim);
+  const double ang = (double)ids[s * 3 + axis] * freq;
+  cs[idx] = make_float2((float)cos(ang), (float)sin(ang));
+}
+
+__global__ void build_selection_kernel(const int* sel_img, int n_img, int T, int* sel_img_out, int* sel_all_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) sel_all_out[i] = i;
+  if (i < n_img) {
+    int v = sel_img ? sel_img[i] : i;
+    sel_img_out[i] = v;
+    sel_all_out[T + i] = T + v;
+  }
+}
+
+// ------------------------------------------------------------------ row gather / scatter (utils.py:240-279)
+template <bool kScatter>
+__global__ void move_rows_kernel(const __nv_bfloat16* __restrict__ src, long lds, const int* __restrict__ ids, int n,
+                                 int vec_per_row, __nv_bfloat16* __restrict__ dst, long ldd) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)n * vec_per_row) return;
+  const int r = (int)(idx / vec_per_row), c = (int)(idx % vec_per_row);
+  const int id = ids[r];
+  if (kScatter)
+    reinterpret_cast<uint4*>(dst + (long)id * ldd)[c] = reinterpret_cast<const uint4*>(src + (long)r * lds)[c];
+  else
+    reinterpret_cast<uint4*>(dst + (long)r * ldd)[c] = reinterpret_cast<const uint4*>(src + (long)id * lds)[c];
+}
+
+// ------------------------------------------------------------------ Euler step (+ velocity-decay reuse)
+// inplace.py:610,655-680,686 and :318: fp32 sample, dt*v rounded to bf16 first (0-dim fp32 x bf16 tensor -> bf16).
+__global__ void euler_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ v,
+                             __nv_bfloat16* __restrict__ out, int M, int vec_per_row, float dt, float dt_direct,
+                             const uint8_t* __restrict__ mask, int vscale_on, float vscale) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * vec_per_row) return;
+  const int m = (int)(idx / vec_per_row);
+  const float d = mask ? (mask[m] ? dt : dt_direct) : dt;
+  float xf[8], vf[8];
+  unpack8(reinterpret_cast<const uint4*>(x)[idx], xf);
+  unpack8(reinterpret_cast<const uint4*>(v)[idx], vf);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float vv = vscale_on ? bf16_round(vf[j] * vscale) : vf[j];
+    xf[j] = xf[j] + bf16_round(d * vv);
+  }
+  reinterpret_cast<uint4*>(out)[idx] = pack8(xf);
+}
+
+// ------------------------------------------------------------------ adaptive region partition (utils.py:305-333)
+// One warp per token; warp-shuffle reductions over the channel axis.
+__global__ void __launch_bounds__(256) arp_similarity_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ v,
+                                                             const __nv_bfloat16* __restrict__ cond, float dt_final,
+                                                             float thr, uint8_t* __restrict__ mask,
+                                                             float* __restrict__ sim_out, int L, int Cch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= L) return;
+  float e[4], c[4];
+  float ss_e = 0.f, ss_c = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = lane + 32 * i;
+    e[i] = 0.f;
+    c[i] = 0.f;
+    if (ch < Cch) {
+      const long o = (long)m * Cch + ch;
+      // one-step x0 estimate, fp32: sample + bf16(dt_final * model_output)   (inplace.py:650)
+      e[i] = __bfloat162float(x[o]) + bf16_round(dt_final * __bfloat162float(v[o]));
+      c[i] = __bfloat162float(cond[o]);
+      ss_e += e[i] * e[i];
+      ss_c += c[i] * c[i];
+    }
+  }
+  ss_e = warp_sum(ss_e);
+  ss_c = warp_sum(ss_c);
+  // F.normalize: fp32 tensor in fp32; the bf16 condition latent in bf16 (norm rounded to bf16, quotient too)
+  const float den_e = fmaxf(sqrtf(ss_e), 1e-12f);
+  const float den_c = fmaxf(bf16_round(sqrtf(ss_c)), bf16_round(1e-12f));
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dot += (e[i] / den_e) * bf16_round(c[i] / den_c);
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    mask[m] = dot <= thr ? 1 : 0;
+    if (sim_out) sim_out[m] = dot;
+  }
+}
+
+// ------------------------------------------------------------------ morphology + ordered compaction
+// utils.py:215-237 (erosion 3x3 cross == 5, dilation 5x5 ones > 0, zero padding) and :345-352 (ascending ids).
+__global__ void __launch_bounds__(1024) morph_compact_kernel(const uint8_t* __restrict__ mask_in,
+                                                             uint8_t* __restrict__ mask_out, int gh, int gw,
+                                                             int erosion_dilation, int* __restrict__ edited,
+                                                             int* __restrict__ unedited, int* __restrict__ counts) {
+  extern __shared__ uint8_t sm[];
+  const int L = gh * gw;
+  uint8_t* a = sm;
+  uint8_t* b = sm + L;
+  __shared__ int warp_tot[32];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) a[i] = mask_in[i] ? 1 : 0;
+  __syncthreads();
+  if (erosion_dilation) {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      const int r = i / gw, c = i % gw;
+      int s = a[i];
+      s += (r > 0) ? a[i - gw] : 0;
+      s += (r < gh - 1) ? a[i + gw] : 0;
+      s += (c > 0) ? a[i - 1] : 0;
+      s += (c < gw - 1) ? a[i + 1] : 0;
+      b[i] = (s == 5) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      const int r = i / gw, c = i % gw;
+      int s = 0;
+      for (int dr = -2; dr <= 2; ++dr) {
+        const int rr = r + dr;
+        if (rr < 0 || rr >= gh) continue;
+        for (int dc = -2; dc <= 2; ++dc) {
+          const int cc = c + dc;
+          if (cc < 0 || cc >= gw) continue;
+          s += b[rr * gw + cc];
+        }
+      }
+      a[i] = (s > 0) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  // ordered compaction: thread t owns the contiguous chunk [t*chunk, (t+1)*chunk)
+  const int chunk = (L + blockDim.x - 1) / blockDim.x;
+  const int beg = threadIdx.x * chunk;
+  const int end = min(beg + chunk, L);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) cnt += a[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;  // exclusive
+    if (lane == 31) counts[0] = wi;
+    if (lane == 31) counts[1] = L - wi;
+  }
+  __syncthreads();
+  int e_pos = warp_tot[warp] + incl - cnt;  // edited tokens before `beg`
+  int u_pos = beg - e_pos;
+  for (int i = beg; i < end; ++i) {
+    if (mask_out) mask_out[i] = a[i];
+    if (a[i]) edited[e_pos++] = i;
+    else unedited[u_pos++] = i;
+  }
+}
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+cudaError_t launch_ln_modulate(const __nv_bfloat16* x, long ldx, const __nv_bfloat16* scale,
+                               const __nv_bfloat16* shift, __nv_bfloat16* out, long ldo, int M, int D,
+                               cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  if (D % 8 || ldx % 8 || ldo % 8) return cudaErrorInvalidValue;
+  ln_modulate_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M, D);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemv_batch(const GemvJob* jobs_dev, int n_jobs, int max_n, cudaStream_t s) {
+  if (n_jobs <= 0) return cudaSuccess;
+  dim3 grid(cdiv(max_n, 8), n_jobs);
+  gemv_batch_kernel<<<grid, 256, 4096 * sizeof(float), s>>>(jobs_dev);  // K <= 4096 (checked by the caller)
+  return cudaGetLastError();
+}
+
+cudaError_t launch_timestep_proj(float t, __nv_bfloat16* out256, cudaStream_t s) {
+  timestep_proj_kernel<<<1, 128, 0, s>>>(t, out256);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add3(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c, __nv_bfloat16* out,
+                        int n, cudaStream_t s) {
+  add3_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, b, c, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rope_table(const float* ids, float2* cs, int S, cudaStream_t s) {
+  if (S <= 0) return cudaSuccess;
+  rope_table_kernel<<<cdiv((long)S * 64, 256), 256, 0, s>>>(ids, cs, S);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_selection(const int* sel_img, int n_img, int T, int* sel_img_out, int* sel_all_out,
+                                   cudaStream_t s) {
+  const int n = n_img > T ? n_img : T;
+  if (n <= 0) return cudaSuccess;
+  build_selection_kernel<<<cdiv(n, 256), 256, 0, s>>>(sel_img, n_img, T, sel_img_out, sel_all_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const __nv_bfloat16* src, long lds, const int* ids, int n, int width,
+                               __nv_bfloat16* dst, long ldd, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (width % 8 || lds % 8 || ldd % 8) return cudaErrorInvalidValue;
+  move_rows_kernel<false><<<cdiv((long)n * (width / 8), 256), 256, 0, s>>>(src, lds, ids, n, width / 8, dst, ldd);
+  return cudaGetLastError();
+}
+cudaError_t launch_scatter_rows(const __nv_bfloat16* src, long lds, const int* ids, int n, int width,
+                                __nv_bfloat16* dst, long ldd, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (width % 8 || lds % 8 || ldd % 8) return cudaErrorInvalidValue;
+  move_rows_kernel<true><<<cdiv((long)n * (width / 8), 256), 256, 0, s>>>(src, lds, ids, n, width / 8, dst, ldd);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_euler(const __nv_bfloat16* x, const __nv_bfloat16* v, __nv_bfloat16* out, int M, int Cch,
+                         float dt, float dt_direct, const uint8_t* mask, int vscale_on, float vscale,
+                         cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  if (Cch % 8) return cudaErrorInvalidValue;
+  euler_kernel<<<cdiv((long)M * (Cch / 8), 256), 256, 0, s>>>(x, v, out, M, Cch / 8, dt, dt_direct, mask, vscale_on,
+                                                             vscale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_arp_similarity(const __nv_bfloat16* x, const __nv_bfloat16* v, const __nv_bfloat16* cond,
+                                  float dt_final, float thr, uint8_t* mask, float* sim_out, int L, int Cch,
+                                  cudaStream_t s) {
+  if (L <= 0) return cudaSuccess;
+  if (Cch > 128) return cudaErrorInvalidValue;
+  arp_similarity_kernel<<<cdiv(L, 8), 256, 0, s>>>(x, v, cond, dt_final, thr, mask, sim_out, L, Cch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_morph_compact(const uint8_t* mask_in, uint8_t* mask_out, int gh, int gw, int erosion_dilation,
+                                 int* edited, int* unedited, int* counts, cudaStream_t s) {
+  const int L = gh * gw;
+  if (L <= 0 || 2 * L > 96 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(morph_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  morph_compact_kernel<<<1, 1024, 2 * L, s>>>(mask_in, mask_out, gh, gw, erosion_dilation, edited, unedited, counts);
+  return cudaGetLastError();
+}
+
+}  // namespace rge

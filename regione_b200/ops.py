@@ -1,0 +1,146 @@
+"""Torch-tensor wrappers over the kernel-level C-ABI entry points (device memory and streams only; no compute here)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, GemmDesc, check, ptr, stream_ptr
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.RegionEB200Error(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.RegionEB200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.dim() >= 2 and t.stride(-1) != 1:
+        raise _lib.RegionEB200Error(f"{name}: innermost dimension must be contiguous")
+
+
+def gemm(a, w, bias=None, *, epilogue=_lib.EPI_STORE, out=None, row_map=None, row_off=0, col_off=0, gate=None,
+         res=None, norm_w=None, rope_cs=None, rope_map=None, rope_off=0):
+    """out[(row_map[m] or m)+row_off, col_off+n] = epilogue(a[M,K] @ w[N,K]^T + bias)."""
+    lib = _lib.load()
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    _req(out, torch.bfloat16, "out")
+    d = GemmDesc()
+    d.A, d.lda = ptr(a), a.stride(0)
+    d.W, d.ldw = ptr(w), w.stride(0)
+    d.bias = ptr(bias)
+    d.M, d.N, d.K = M, N, K
+    d.epilogue = epilogue
+    d.out, d.ldo = ptr(out), out.stride(0)
+    d.row_map, d.row_off, d.col_off = ptr(row_map), row_off, col_off
+    d.gate, d.res, d.ldr = ptr(gate), ptr(res), (res.stride(0) if res is not None else 0)
+    d.norm_w, d.rope_cs = ptr(norm_w), ptr(rope_cs)
+    d.rope_map, d.rope_off = ptr(rope_map), rope_off
+    check(lib.rge_op_gemm(C.byref(d), stream_ptr()), "rge_op_gemm")
+    return out
+
+
+def attention(q, k, v, heads: int, out=None, scale: float | None = None):
+    """q [Sq, H*128], k/v [Skv, H*128] -> out [Sq, H*128]."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, torch.bfloat16, n)
+    if out is None:
+        out = torch.empty(q.shape[0], heads * 128, dtype=torch.bfloat16, device=q.device)
+    d = AttnDesc()
+    d.Q, d.ldq = ptr(q), q.stride(0)
+    d.K, d.ldk = ptr(k), k.stride(0)
+    d.V, d.ldv = ptr(v), v.stride(0)
+    d.O, d.ldo = ptr(out), out.stride(0)
+    d.Sq, d.Skv, d.H = q.shape[0], k.shape[0], heads
+    d.scale = scale if scale is not None else 128 ** -0.5
+    check(lib.rge_op_attention(C.byref(d), stream_ptr()), "rge_op_attention")
+    return out
+
+
+def ln_modulate(x, scale, shift, out=None):
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    M, Dm = x.shape
+    check(lib.rge_op_ln_modulate(ptr(x), x.stride(0), ptr(scale), ptr(shift), ptr(out), out.stride(0), M, Dm,
+                                 stream_ptr()), "rge_op_ln_modulate")
+    return out
+
+
+def rope_table(ids: torch.Tensor) -> torch.Tensor:
+    """ids fp32 [S,3] -> fp32 [S,64,2] (cos, sin)."""
+    lib = _lib.load()
+    _req(ids, torch.float32, "ids")
+    ids = ids.contiguous()
+    cs = torch.empty(ids.shape[0], 64, 2, dtype=torch.float32, device=ids.device)
+    check(lib.rge_op_rope_table(ptr(ids), ptr(cs), ids.shape[0], stream_ptr()), "rge_op_rope_table")
+    return cs
+
+
+def gather_rows(src, ids, out=None):
+    lib = _lib.load()
+    _req(src, torch.bfloat16, "src"); _req(ids, torch.int32, "ids")
+    n, width = ids.numel(), src.shape[1]
+    if out is None:
+        out = torch.empty(n, width, dtype=torch.bfloat16, device=src.device)
+    check(lib.rge_gather_rows(ptr(src), src.stride(0), ptr(ids), n, width, ptr(out), out.stride(0), stream_ptr()),
+          "rge_gather_rows")
+    return out
+
+
+def scatter_rows(src, ids, dst):
+    lib = _lib.load()
+    _req(src, torch.bfloat16, "src"); _req(ids, torch.int32, "ids"); _req(dst, torch.bfloat16, "dst")
+    n, width = ids.numel(), src.shape[1]
+    check(lib.rge_scatter_rows(ptr(src), src.stride(0) if n else width, ptr(ids), n, width, ptr(dst), dst.stride(0),
+                               stream_ptr()), "rge_scatter_rows")
+    return dst
+
+
+def euler(x, v, dt: float, dt_direct: float = 0.0, edited_mask=None, reuse_ratio: float | None = None, out=None):
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x"); _req(v, torch.bfloat16, "v")
+    x = x.contiguous(); v = v.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    M, ch = x.shape
+    check(lib.rge_euler(ptr(x), ptr(v), ptr(out), M, ch, dt, dt_direct, ptr(edited_mask),
+                        0 if reuse_ratio is None else 1, 0.0 if reuse_ratio is None else reuse_ratio, stream_ptr()),
+          "rge_euler")
+    return out
+
+
+def partition(x, v, cond, dt_final: float, threshold: float, want_sim: bool = False):
+    """Raw (pre-morphology) edited mask uint8 [L] (+ fp32 similarity if requested)."""
+    lib = _lib.load()
+    for t, n in ((x, "x"), (v, "v"), (cond, "cond")):
+        _req(t, torch.bfloat16, n)
+    x = x.contiguous(); v = v.contiguous(); cond = cond.contiguous()
+    L, ch = x.shape
+    mask = torch.empty(L, dtype=torch.uint8, device=x.device)
+    sim = torch.empty(L, dtype=torch.float32, device=x.device) if want_sim else None
+    check(lib.rge_partition(ptr(x), ptr(v), ptr(cond), dt_final, threshold, ptr(mask), ptr(sim), L, ch,
+                            stream_ptr()), "rge_partition")
+    return (mask, sim) if want_sim else mask
+
+
+def compact(mask, grid_h: int, grid_w: int, erosion_dilation: bool):
+    """-> (final mask uint8 [L], edited_ids int32 [n_e], unedited_ids int32 [L-n_e]); one D2H sync for the counts
+    (the reference syncs at the same point through boolean indexing, utils.py:347)."""
+    lib = _lib.load()
+    _req(mask, torch.uint8, "mask")
+    L = grid_h * grid_w
+    dev = mask.device
+    out_mask = torch.empty(L, dtype=torch.uint8, device=dev)
+    edited = torch.empty(L, dtype=torch.int32, device=dev)
+    unedited = torch.empty(L, dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    check(lib.rge_compact(ptr(mask), ptr(out_mask), grid_h, grid_w, 1 if erosion_dilation else 0, ptr(edited),
+                          ptr(unedited), ptr(counts), stream_ptr()), "rge_compact")
+    n_e = int(counts[0].item())
+    return out_mask, edited[:n_e], unedited[: L - n_e]
