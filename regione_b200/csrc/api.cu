@@ -387,7 +387,7 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
 
 int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
                  float timestep_x1000, void* v_out, int32_t n_out, void* stream) {
-  if (!h || !v_out || (n_img > 0 && !x_in)) return fail(RGE_ERR_INVALID, "rge_dit_step: null argument");
+  if (!h || (n_out > 0 && !v_out) || (n_img > 0 && !x_in)) return fail(RGE_ERR_INVALID, "rge_dit_step: null argument");
   if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_dit_step: bad pass %d", pass);
   if (!h->finalized || !h->begun[pass]) return fail(RGE_ERR_STATE, "rge_dit_step: rge_begin_image not called");
   if (n_img < 0 || n_img > h->L + h->C || (!sel && n_img != h->L + h->C))

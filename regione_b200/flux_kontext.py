@@ -1,0 +1,320 @@
+"""FLUX.1-Kontext variant of the plugin: `warp_modules` / `unwarp_modules`, the patched pipeline loop, the patched
+transformer forward and the patched scheduler step — the host side of RegionE/FluxKontext/inplace.py, with every
+tensor operation delegated to the CUDA library (regione_b200/csrc) through the C ABI.
+
+Host-side departures from the reference, none of which change results:
+  * AVDC decisions are planned before the loop from the host copy of the schedule (manager.plan_steps), removing the
+    1-2 device->host syncs per step of inplace.py:301-308; the only sync left per image is the edited-token count
+    after the partition (the reference syncs there too, utils.py:347);
+  * the K/V cache, attention processors' state and all workspaces live inside the library handle (engine.FluxEngine);
+  * latents are handled as 2-D [tokens, channels] views of the reference's [1, tokens, channels].
+"""
+from __future__ import annotations
+
+import types
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import FluxEngine
+from .manager import RegionManager, plan_steps
+from .params import GAMMA, SCALAR_ROUNDS_TO_BF16
+
+gamma = GAMMA["FluxKontextPipeline"]          # inplace.py:47-50
+MANAGER = RegionManager()                     # inplace.py:51 (module-global singleton, one pipeline per process)
+
+
+def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.15):
+    """Linear interpolation of the schedule shift mu in the token count (utils.py:38-48)."""
+    slope = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    return base_shift + slope * (image_seq_len - base_seq_len)
+
+
+def _scalar(s: torch.Tensor) -> float:
+    """A 0-dim fp32 schedule scalar as the CUDA reference would apply it to a bf16 tensor (params.py)."""
+    return float(s.to(torch.bfloat16)) if SCALAR_ROUNDS_TO_BF16 else float(s)
+
+
+class RegionEB200AttnProcessor:
+    """Placeholder installed on every attention module by `warp_modules` (the reference installs
+    RegoionEFluxAttnProcessor2_0 there, inplace.py:58-61). The per-layer K/V cache that processor owned now lives in
+    the library handle, and attention runs inside `rge_dit_step`, so calling the processor is an error."""
+
+    def __init__(self, single: bool):
+        self.single = single
+
+    def __call__(self, *a, **k):
+        raise RuntimeError("regione_b200: attention runs inside the CUDA library (rge_dit_step), not per module")
+
+
+# ---------------------------------------------------------------------------------------------- patched scheduler
+class RegionESchedulerMixin:
+    """`RegionEFlowMatchEulerDiscreteScheduler.step` (inplace.py:581-691) over the library kernels."""
+
+    def _host_sigmas(self):
+        hs = getattr(self, "_regione_host_sigmas", None)
+        if hs is None or hs.shape != self.sigmas.shape:
+            hs = self.sigmas.detach().to("cpu", torch.float32)
+            self._regione_host_sigmas = hs
+        return hs
+
+    def set_timesteps(self, *a, **k):
+        super().set_timesteps(*a, **k)
+        self._regione_host_sigmas = None
+
+    def step(self, model_output, timestep, sample, *args, return_dict=True, reuse_ratio=None, **kwargs):
+        if isinstance(timestep, int):
+            raise ValueError("pass one of scheduler.timesteps, not an integer index")            # :594-605
+        if self.step_index is None:
+            self._init_step_index(timestep)                                                      # :606-607
+        M = MANAGER
+        sig = self._host_sigmas()
+        idx = self.step_index
+        sigma, sigma_next = sig[idx], sig[idx + 1]
+        dt_final = dt_direct = None
+        if M.current_step == M.warmup_step - 1:                                                  # :630-634
+            M.prev_refresh_step = M.refresh_step_real_time.pop(0) - 1
+            dt_final = sig[-1] - sigma
+            dt_direct = sig[M.prev_refresh_step] - sigma
+        elif M.prev_refresh_step is not None and M.current_step == M.prev_refresh_step and M.refresh_step_real_time:
+            M.next_refresh_step = M.refresh_step_real_time.pop(0) - 1                             # :636-639
+            dt_direct = sig[M.next_refresh_step] - sigma
+        dt = sigma_next - sigma                                                                  # :641
+        shape = sample.shape
+        ch = shape[-1]
+        x, v = sample.reshape(-1, ch), model_output.reshape(-1, ch)
+        ratio = None if reuse_ratio is None else _scalar(reuse_ratio)
+        if M.current_step == M.warmup_step - 1:                                                  # :648-663
+            raw = ops.partition(x, v, M.condition_latent.reshape(-1, ch), _scalar(dt_final), float(M.threshold))
+            gh = M.height // (M.patch_size * M.vae_scale_factor)
+            gw = M.width // (M.patch_size * M.vae_scale_factor)
+            M.edited_mask, M.edited_ids, M.unedited_ids = ops.compact(raw, gh, gw, bool(M.erosion_dilation))
+            prev = ops.euler(x, v, _scalar(dt), _scalar(dt_direct), edited_mask=M.edited_mask)
+        elif M.prev_refresh_step is not None and M.current_step == M.prev_refresh_step:          # :665-677
+            prev = ops.euler(x, v, _scalar(dt), _scalar(dt_direct) if dt_direct is not None else 0.0,
+                             edited_mask=M.edited_mask)
+        else:                                                                                    # :680, :318
+            prev = ops.euler(x, v, _scalar(dt), reuse_ratio=ratio)
+        self._step_index += 1                                                                    # :683
+        prev = prev.reshape(shape)
+        if not return_dict:
+            return (prev,)
+        return types.SimpleNamespace(prev_sample=prev)
+
+
+# ---------------------------------------------------------------------------------------------- patched forward
+def _get_engine(transformer, T, L, C, n_pass=1) -> FluxEngine:
+    cache = transformer.__dict__.setdefault("_regione_b200_engines", {})
+    key = (T, L, C, n_pass)
+    eng = cache.get(key)
+    if eng is None:
+        for old in list(cache.values()):   # one resident KV cache per transformer: shapes rarely change
+            old.close()
+        cache.clear()
+        eng = FluxEngine(transformer, T, L, C, n_pass)
+        cache[key] = eng
+    return eng
+
+
+def RegionEFluxTransformer2DModelforward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None,
+                                         timestep=None, img_ids=None, txt_ids=None, guidance=None,
+                                         joint_attention_kwargs=None, controlnet_block_samples=None,
+                                         controlnet_single_block_samples=None, return_dict=True,
+                                         controlnet_blocks_repeat=False):
+    """Same signature as the reference's patched forward (inplace.py:413-427). Mode selection follows the
+    processor's rule (inplace.py:717-732): all L+C image tokens present -> FULL (cache rows of every token are
+    rewritten); fewer -> REGION with selection = MANAGER.edited_ids."""
+    if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
+        raise NotImplementedError("regione_b200: ControlNet residuals are outside the hot path")
+    if joint_attention_kwargs and "ip_adapter_image_embeds" in joint_attention_kwargs:
+        raise NotImplementedError("regione_b200: IP-Adapter is outside the hot path")
+    engine = self.__dict__.get("_regione_b200_engine")
+    if engine is None:
+        raise RuntimeError("regione_b200: no image in flight — the pipeline loop calls begin_image first")
+    if hidden_states.shape[0] != 1:
+        raise NotImplementedError("regione_b200: batch size must be 1 (the reference's partition is B=1, SURVEY C-10)")
+    M = MANAGER
+    t_x1000 = float((timestep.to(hidden_states.dtype) * 1000).reshape(-1)[0])                    # :471
+    x = hidden_states[0]
+    full = x.shape[0] == M.latent_length + M.condition_length
+    if full:
+        sel, n_out = None, M.latent_length
+    else:
+        if M.edited_ids is None or x.shape[0] != M.edited_ids.numel():
+            raise RuntimeError("regione_b200: region step without a matching edited-token selection")
+        sel, n_out = M.edited_ids, x.shape[0]
+    out = engine.step(x, sel, t_x1000, n_out)[None]
+    if not return_dict:
+        return (out,)
+    return types.SimpleNamespace(sample=out)
+
+
+# ---------------------------------------------------------------------------------------------- patched pipeline
+class RegionEFluxKontextPipelineMixin:
+    """`RegionEFluxKontextPipeline.__call__` (inplace.py:76-410). Latent-space entry: pass packed `latents` [1,L,64],
+    packed `image_latents` [1,C,64], `prompt_embeds` [1,T,ctx] and `pooled_prompt_embeds` [1,pooled] (bf16, CUDA) with
+    `output_type="latent"`; pixel-space pre/post-processing (image processor, text encoders, VAE) stays the host
+    pipeline's own code and is used when the pipeline provides it."""
+
+    @torch.no_grad()
+    def __call__(self, image=None, prompt=None, prompt_2=None, height=None, width=None, num_inference_steps=28,
+                 guidance_scale=3.5, num_images_per_prompt=1, generator=None, latents=None, prompt_embeds=None,
+                 pooled_prompt_embeds=None, output_type="pil", return_dict=True, joint_attention_kwargs=None,
+                 max_sequence_length=512, max_area=1024 ** 2, _auto_resize=True, image_latents=None,
+                 true_cfg_scale=1.0, **unused):
+        assert num_inference_steps == MANAGER.inference_step, "num_inference_steps should be equal to 28"   # :112
+        if true_cfg_scale > 1:
+            raise NotImplementedError("regione_b200: true-CFG needs a second pass; not wired for FluxKontext yet")
+        device = self._execution_device
+        multiple_of = self.vae_scale_factor * 2
+        self._guidance_scale = guidance_scale
+        self._joint_attention_kwargs = joint_attention_kwargs
+        self._interrupt = False
+        if image_latents is None:
+            # pixel-space path: the pipeline's own preprocessing / encoders, same calls as inplace.py:113-226
+            if not hasattr(self, "encode_prompt") or not hasattr(self, "prepare_latents"):
+                raise RuntimeError("this pipeline has no encoders/VAE: pass latents, image_latents and prompt embeds")
+            if image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):
+                img = image[0] if isinstance(image, list) else image
+                ih, iw = self.image_processor.get_default_height_width(img)
+                if _auto_resize:
+                    from .resolutions import nearest_kontext_resolution
+                    iw, ih = nearest_kontext_resolution(iw / ih)
+                iw, ih = iw // multiple_of * multiple_of, ih // multiple_of * multiple_of
+                image = self.image_processor.resize(image, ih, iw)
+                image = self.image_processor.preprocess(image, ih, iw)
+                height, width = image.shape[-2], image.shape[-1]
+            prompt_embeds, pooled_prompt_embeds, text_ids = self.encode_prompt(
+                prompt=prompt, prompt_2=prompt_2, prompt_embeds=prompt_embeds,
+                pooled_prompt_embeds=pooled_prompt_embeds, device=device, num_images_per_prompt=num_images_per_prompt,
+                max_sequence_length=max_sequence_length, lora_scale=None)
+            nch = self.transformer.config.in_channels // 4
+            latents, image_latents, latent_ids, image_ids = self.prepare_latents(
+                image, 1, nch, height, width, prompt_embeds.dtype, device, generator, latents)
+            if image_ids is not None:
+                latent_ids = torch.cat([latent_ids, image_ids], dim=0)
+        else:
+            from .standin import latent_image_ids
+            if height is None or width is None:
+                raise ValueError("height and width are required with packed latents")
+            gh, gw = height // multiple_of, width // multiple_of
+            assert latents.shape[1] == gh * gw and image_latents.shape[1] == gh * gw, "latents do not match H x W"
+            text_ids = torch.zeros(prompt_embeds.shape[1], 3, device=device)
+            latent_ids = torch.cat([latent_image_ids(gh, gw, 0.0, device), latent_image_ids(gh, gw, 1.0, device)])
+        # timesteps (inplace.py:229-244)
+        sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
+        cfg = self.scheduler.config
+        mu = calculate_shift(latents.shape[1], cfg.get("base_image_seq_len", 256), cfg.get("max_image_seq_len", 4096),
+                             cfg.get("base_shift", 0.5), cfg.get("max_shift", 1.15))
+        self.scheduler.set_timesteps(sigmas=sigmas, device=device, mu=mu)
+        self.scheduler.set_begin_index(0)   # known start: spares _init_step_index's device lookup (:606-607)
+        self.scheduler._step_index = 0
+        latents = self.regione_denoise(latents, image_latents, latent_ids, text_ids, prompt_embeds,
+                                       pooled_prompt_embeds, guidance_scale, height, width)
+        if output_type == "latent":
+            image = latents
+        else:
+            x = self._unpack_latents(latents, height, width, self.vae_scale_factor)
+            x = (x / self.vae.config.scaling_factor) + self.vae.config.shift_factor
+            image = self.image_processor.postprocess(self.vae.decode(x, return_dict=False)[0], output_type=output_type)
+        if not return_dict:
+            return (image,)
+        return types.SimpleNamespace(images=image)
+
+    def regione_denoise(self, latents, image_latents, latent_ids, text_ids, prompt_embeds, pooled_prompt_embeds,
+                        guidance_scale, height, width):
+        """The hot loop, inplace.py:287-392."""
+        M = MANAGER
+        N = M.inference_step
+        sch = self.scheduler
+        ts_host = sch.timesteps.detach().to("cpu", torch.float32)
+        x = latents[0]
+        cond = image_latents[0]
+        L, C, T = x.shape[0], cond.shape[0], text_ids.shape[0]
+        engine = _get_engine(self.transformer, T, L, C)
+        self.transformer.__dict__["_regione_b200_engine"] = engine
+        M.refresh(x, cond, latent_ids, text_ids, 2, self.vae_scale_factor, height, width)          # :287
+        g_x1000 = float(torch.tensor(guidance_scale, dtype=torch.float32).to(x.dtype) * 1000)     # :250, :473
+        engine.begin_image(text_ids, latent_ids, prompt_embeds[0], pooled_prompt_embeds[0], g_x1000)
+        guidance = torch.full([1], guidance_scale, dtype=torch.float32)
+        plan = plan_steps(ts_host, gamma, M)                                                      # :295-313
+        cache = None
+        record = bool(getattr(self, "regione_record", False))   # tests: keep per-step tensors
+        self.regione_trace = {"modes": [], "latents": [], "noise_pred": []}
+        for i in range(N):
+            assert i == M.current_step                                                            # :293
+            t = ts_host[i]
+            skip, ratio = plan[i]
+            if skip:                                                                              # :315-318
+                if cache.shape[0] != x.shape[0]:
+                    cache = ops.gather_rows(cache, M.edited_ids)
+                x = sch.step(cache, t, x, return_dict=False, reuse_ratio=ratio)[0]
+                self.regione_trace["modes"].append("SKIP")
+            else:
+                cur = M.current_step
+                full = cur <= M.warmup_step - 1 or cur > N - M.post_step - 1 or cur == M.prev_refresh_step   # :331
+                x_in = torch.cat([x, cond], dim=0) if full else x
+                timestep = t.expand(1).to(x.dtype)                                                # :334
+                noise_pred = self.transformer(hidden_states=x_in[None], timestep=timestep / 1000, guidance=guidance,
+                                              pooled_projections=pooled_prompt_embeds,
+                                              encoder_hidden_states=prompt_embeds, txt_ids=text_ids,
+                                              img_ids=latent_ids, joint_attention_kwargs=None,
+                                              return_dict=False)[0]
+                noise_pred = noise_pred[0, : x.shape[0]]                                          # :347
+                cache = noise_pred                                                                # :365
+                x = sch.step(noise_pred, t, x, return_dict=False)[0]                               # :369
+                self.regione_trace["modes"].append("FULL" if full else "REGION")
+            x, latent_ids = M.step(x, latent_ids)                                                 # :392
+            if record:
+                self.regione_trace["latents"].append(x.clone())
+                self.regione_trace["noise_pred"].append(cache.clone())
+        self.regione_trace["edited_ids"] = M.edited_ids
+        self.regione_trace["unedited_ids"] = M.unedited_ids
+        return x[None]
+
+
+def warp_modules(pipeline, **args):
+    """inplace.py:53-62: install the RegionE loop, scheduler, forward and processors on a live pipeline object."""
+    if "_regione_b200_saved" in pipeline.__dict__:
+        unwarp_modules(pipeline)
+    MANAGER.set_parameters(args)
+    tr = pipeline.transformer
+    saved = {
+        "cls": pipeline.__class__,
+        "scheduler": pipeline.scheduler,
+        "forward": tr.__dict__.get("forward"),
+        "processors": [getattr(b.attn, "processor", None)
+                       for b in list(tr.transformer_blocks) + list(tr.single_transformer_blocks)],
+    }
+    pipeline.__dict__["_regione_b200_saved"] = saved
+    pipeline.__class__ = type("RegionEFluxKontextPipeline", (RegionEFluxKontextPipelineMixin, saved["cls"]), {})
+    sch_cls = type("RegionEFlowMatchEulerDiscreteScheduler", (RegionESchedulerMixin, saved["scheduler"].__class__), {})
+    pipeline.scheduler = sch_cls.from_config(saved["scheduler"].config)
+    tr.forward = types.MethodType(RegionEFluxTransformer2DModelforward, tr)
+    for block in tr.transformer_blocks:
+        block.attn.set_processor(RegionEB200AttnProcessor(False))
+    for block in tr.single_transformer_blocks:
+        block.attn.set_processor(RegionEB200AttnProcessor(True))
+    return pipeline
+
+
+def unwarp_modules(pipeline):
+    """inplace.py:65-73: restore the vanilla class, scheduler, forward and processors; frees the library handle."""
+    saved = pipeline.__dict__.pop("_regione_b200_saved", None)
+    if saved is None:
+        return pipeline
+    tr = pipeline.transformer
+    pipeline.__class__ = saved["cls"]
+    pipeline.scheduler = saved["scheduler"].__class__.from_config(saved["scheduler"].config)
+    if saved["forward"] is None:
+        tr.__dict__.pop("forward", None)
+    else:
+        tr.forward = saved["forward"]
+    blocks = list(tr.transformer_blocks) + list(tr.single_transformer_blocks)
+    for b, p in zip(blocks, saved["processors"]):
+        b.attn.set_processor(p)
+    for eng in tr.__dict__.pop("_regione_b200_engines", {}).values():
+        eng.close()
+    tr.__dict__.pop("_regione_b200_engine", None)
+    return pipeline

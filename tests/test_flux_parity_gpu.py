@@ -1,0 +1,112 @@
+"""Parity of the CUDA hot path (through RegionEHelper / the C ABI) against the CPU oracle on identical seeded inputs.
+
+Gate (BASELINE.json north_star): relative L2 <= 1e-2 on bf16 latents, region masks bit-exact.
+"""
+import pytest
+import torch
+
+from oracle.flux import FluxOracle
+from oracle.loop import run_regione
+from oracle.schedule import GAMMA
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def _run_both(arch, grid, txt_len, rho, params, seed=7):
+    from regione_b200 import RegionEHelper
+    from regione_b200 import synthetic as syn
+    from regione_b200.standin import latent_image_ids
+
+    gh, gw = grid
+    pipe = syn.build_pipeline(arch, seed=110, device="cpu")
+    weights = {k: v.detach().clone() for k, v in pipe.transformer.state_dict().items()}
+    inp = syn.make_inputs(seed, gh, gw, txt_len, arch["ctx_dim"], arch["pooled_dim"], rho=rho)
+    # oracle on the CPU
+    model = FluxOracle(weights, arch["heads"], arch["n_double"], arch["n_single"], arch["guidance_embeds"])
+    ids = torch.cat([latent_image_ids(gh, gw, 0.0), latent_image_ids(gh, gw, 1.0)])
+    o_params = dict(num_inference_steps=28, **params)
+    ref, ref_tr = run_regione(model, o_params, GAMMA["FluxKontext"], inp["latents"], inp["image_latents"], ids,
+                              torch.zeros(txt_len, 3), inp["prompt_embeds"], inp["pooled_prompt_embeds"], 2.5,
+                              inp["height"], inp["width"], record=True)
+    # CUDA path through the plugin surface
+    pipe.transformer.to("cuda")
+    helper = RegionEHelper(pipe)
+    helper.set_params(**params)
+    helper.enable()
+    pipe = helper.pipeline
+    pipe.regione_record = True
+    cu = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items() if k != "intended_mask"}
+    out = pipe(guidance_scale=2.5, num_inference_steps=28, output_type="latent", return_dict=False, **cu)[0]
+    torch.cuda.synchronize()
+    tr = pipe.regione_trace
+    helper.disable()
+    return ref, ref_tr, out, tr
+
+
+def _check(ref, ref_tr, out, tr):
+    assert tr["modes"] == ref_tr["modes"]
+    e_ref = ref_tr["edited_ids"].squeeze(0).to(torch.int32)
+    u_ref = ref_tr["unedited_ids"].squeeze(0).to(torch.int32)
+    margin = float((ref_tr["similarity"] - 0.0).abs().min()) if "similarity" in ref_tr else float("nan")
+    assert torch.equal(tr["edited_ids"].cpu(), e_ref), f"edited ids differ (similarity margin info {margin})"
+    assert torch.equal(tr["unedited_ids"].cpu(), u_ref)
+    worst = 0.0
+    for i, (a, b) in enumerate(zip(tr["noise_pred"], ref_tr["noise_pred"])):
+        if ref_tr["modes"][i] == "SKIP":
+            continue
+        err = rel_l2(a, b[0])
+        worst = max(worst, err)
+        assert err <= TOL, f"step {i} ({ref_tr['modes'][i]}): velocity rel-L2 {err:.3e} > {TOL}"
+    for i, (a, b) in enumerate(zip(tr["latents"], ref_tr["latents"])):
+        err = rel_l2(a, b[0])
+        assert err <= TOL, f"step {i}: latent rel-L2 {err:.3e} > {TOL}"
+    final = rel_l2(out, ref)
+    assert final <= TOL, f"final latent rel-L2 {final:.3e}"
+    return worst, final
+
+
+DEFAULT = dict(warmup_step=6, post_step=2, refresh_step="16", threshold=0.88, cache_threshold=0.04,
+               erosion_dilation=True)
+
+
+def test_tiny_flux_default_schedule():
+    from regione_b200 import synthetic as syn
+    worst, final = _check(*_run_both(syn.TINY, (16, 16), 32, 0.25, DEFAULT))
+    print(f"tiny: worst velocity rel-L2 {worst:.3e}, final latent rel-L2 {final:.3e}")
+
+
+def test_ragged_grid_and_text_length():
+    """Non-square grid, token counts that are not tile multiples, several refresh steps, no morphology."""
+    from regione_b200 import synthetic as syn
+    params = dict(warmup_step=4, post_step=3, refresh_step="10,18", threshold=0.88, cache_threshold=0.01,
+                  erosion_dilation=False)
+    _check(*_run_both(syn.TINY, (12, 20), 40, 0.4, params, seed=11))
+
+
+def test_all_tokens_edited():
+    """rho = 1: empty unedited set."""
+    from regione_b200 import synthetic as syn
+    ref, ref_tr, out, tr = _run_both(syn.TINY, (16, 16), 32, 1.0, DEFAULT, seed=3)
+    assert tr["unedited_ids"].numel() == 0
+    _check(ref, ref_tr, out, tr)
+
+
+def test_no_token_edited():
+    """rho = 0 without salt noise would still leave stray pixels; with erosion they vanish -> empty edited set."""
+    from regione_b200 import synthetic as syn
+    ref, ref_tr, out, tr = _run_both(syn.TINY, (16, 16), 32, 0.0, DEFAULT, seed=5)
+    assert tr["edited_ids"].numel() == ref_tr["edited_ids"].numel()
+    _check(ref, ref_tr, out, tr)
+
+
+def test_wider_model_three_heads():
+    from regione_b200 import synthetic as syn
+    arch = dict(syn.TINY, dim=768, heads=6, n_double=1, n_single=2, ctx_dim=256)
+    _check(*_run_both(arch, (16, 16), 64, 0.25, DEFAULT, seed=13))

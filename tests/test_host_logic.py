@@ -1,0 +1,136 @@
+"""CPU tests of the host side: plugin surface, manager validation, the zero-sync planner against the golden schedule
+produced by the reference's own code, and the C-ABI library (loads, exports every declared symbol)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from regione_b200 import RegionEHelper, _lib, helper, params
+from regione_b200 import flux_kontext as fk
+from regione_b200 import standin
+from regione_b200.manager import RegionManager, plan_steps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pipe():
+    arch = dict(dim=256, heads=2, n_double=1, n_single=1, mlp_ratio=4, in_channels=64, ctx_dim=64, pooled_dim=32)
+    return standin.FluxKontextPipeline(standin.FluxTransformer2DModel(**arch))
+
+
+def test_helper_surface_matches_reference():
+    """RegionE/tool/RegionE.py:9-51."""
+    pipe = _pipe()
+    h = RegionEHelper(pipe)
+    assert h.name == "FluxKontextPipeline"
+    assert h.config is helper.config["FluxKontextPipeline"]          # shared, mutable defaults (:13)
+    assert h.config["threshold"] == 0.93 and h.config["cache_threshold"] == 0.04
+    saved = dict(h.config)
+    try:
+        h.set_params(threshold=0.88, cache_threshold=0.01)
+        assert h.config["threshold"] == 0.88 and h.config["warmup_step"] == 6
+        with pytest.raises(AssertionError):
+            h.set_params(num_inference_steps=20)
+    finally:
+        h.config.update(saved)
+    for name in ("FluxKontextPipeline", "Step1XEditPipeline", "Step1XEditPipelineV1P2", "QwenImageEditPipeline",
+                 "QwenImageEditPlusPipeline"):
+        assert params.DEFAULTS[name]["num_inference_steps"] == 28 and len(params.GAMMA[name]) == 27
+
+    class Unknown:
+        pass
+    with pytest.raises(KeyError):
+        RegionEHelper(Unknown())
+
+
+def test_enable_disable_patches_and_restores():
+    """inplace.py:53-73: class swap, scheduler swap, forward override, processors."""
+    pipe = _pipe()
+    base_cls, base_sched = pipe.__class__, pipe.scheduler.__class__
+    h = RegionEHelper(pipe)
+    h.enable()
+    assert pipe.__class__.__name__ == "RegionEFluxKontextPipeline" and isinstance(pipe, base_cls)
+    assert pipe.scheduler.__class__.__name__ == "RegionEFlowMatchEulerDiscreteScheduler"
+    assert "forward" in pipe.transformer.__dict__
+    procs = [b.attn.processor for b in list(pipe.transformer.transformer_blocks) +
+             list(pipe.transformer.single_transformer_blocks)]
+    assert [p.single for p in procs] == [False, True]
+    with pytest.raises(RuntimeError):
+        procs[0]()
+    assert fk.MANAGER.refresh_step == [16, 27] and fk.MANAGER.warmup_step == 6
+    h.disable()
+    assert pipe.__class__ is base_cls and pipe.scheduler.__class__ is base_sched
+    assert "forward" not in pipe.transformer.__dict__
+    assert all(b.attn.processor is None for b in pipe.transformer.transformer_blocks)
+
+
+def test_product_fails_loudly_without_cuda():
+    """No CPU fallback: CPU weights / tensors are rejected before any compute."""
+    pipe = _pipe()
+    pipe.transformer.init_synthetic(1, "cpu")
+    h = RegionEHelper(pipe)
+    h.enable()
+    try:
+        inp = dict(latents=torch.zeros(1, 16, 64, dtype=torch.bfloat16),
+                   image_latents=torch.zeros(1, 16, 64, dtype=torch.bfloat16),
+                   prompt_embeds=torch.zeros(1, 8, 64, dtype=torch.bfloat16),
+                   pooled_prompt_embeds=torch.zeros(1, 32, dtype=torch.bfloat16), height=64, width=64)
+        with pytest.raises(_lib.RegionEB200Error):
+            pipe(output_type="latent", **inp)
+    finally:
+        h.disable()
+
+
+def test_manager_validation_matches_reference():
+    """utils.py:390-402."""
+    m = RegionManager()
+    base = dict(num_inference_steps=28, warmup_step=6, post_step=2, threshold=0.88, cache_threshold=0.04,
+                erosion_dilation=True)
+    m.set_parameters(dict(base, refresh_step="16"))
+    assert m.refresh_step == [16, 27]
+    m.set_parameters(dict(base, refresh_step="20,10"))
+    assert m.refresh_step == [10, 20, 27]
+    for bad in (dict(refresh_step="7"), dict(refresh_step="26"), dict(refresh_step="10,11"),
+                dict(refresh_step="16", num_inference_steps=20), dict(refresh_step="16", warmup_step=0)):
+        with pytest.raises(AssertionError):
+            m.set_parameters(dict(base, **bad))
+
+
+def test_planner_matches_reference_schedule(golden_dir):
+    """plan_steps == the decisions the reference's own loop code takes (tests/golden/schedule.pt)."""
+    g = torch.load(os.path.join(golden_dir, "schedule.pt"), weights_only=False)
+    assert torch.equal(torch.tensor(params.GAMMA["FluxKontextPipeline"], dtype=torch.float16), g["gamma"])
+    for p in g["plans"]:
+        m = RegionManager()
+        m.set_parameters(dict(num_inference_steps=28, threshold=0.88, erosion_dilation=True, **p["params"]))
+        plan = plan_steps(p["timesteps"], params.GAMMA["FluxKontextPipeline"], m)
+        assert [s for s, _ in plan] == [st["mode"] == "SKIP" for st in p["steps"]], p["params"]
+        for (skip, ratio), st in zip(plan, p["steps"]):
+            if skip:
+                assert float(ratio) == st["ratio"]
+
+
+def test_standin_scheduler_schedule():
+    s = standin.FlowMatchEulerDiscreteScheduler()
+    import numpy as np
+    s.set_timesteps(sigmas=np.linspace(1.0, 1 / 28, 28), mu=fk.calculate_shift(4096))
+    assert s.sigmas.shape == (29,) and float(s.sigmas[-1]) == 0.0
+    assert abs(float(s.timesteps[5]) - 935.6) < 0.05 and abs(float(s.timesteps[27]) - 104.7) < 0.05
+    assert abs(fk.calculate_shift(4096) - 1.15) < 1e-9 and abs(fk.calculate_shift(256) - 0.5) < 1e-9
+
+
+def test_c_abi_library_loads_and_exports_declared_symbols():
+    lib = _lib.load()
+    assert lib.rge_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "regione_b200.h")).read()
+    declared = set(re.findall(r"\b(rge_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rge_handle"}
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.library_path())
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/regione_b200.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    # argument validation happens before any CUDA call
+    assert lib.rge_op_gemm(None, None) == -1 and b"null" in lib.rge_last_error()
