@@ -20,6 +20,28 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
+// Optional per-class timing (bench.py's roofline): CUDA events around every GEMM / attention launch of the engine.
+enum { PC_GEMM = 0, PC_ATTN = 1, PC_NCLS = 2 };
+struct ProfRec { int cls; double work; cudaEvent_t a, b; };
+bool g_prof = false;
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_pool.empty()) { e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  cudaStream_t st; int cls; double work; cudaEvent_t a;
+  ProfScope(cudaStream_t s, int c, double w) : st(s), cls(c), work(w), a(nullptr) {
+    if (g_prof) { a = prof_event(); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEvent_t b = prof_event(); cudaEventRecord(b, st); g_recs.push_back(ProfRec{cls, work, a, b}); }
+  }
+};
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -73,6 +95,25 @@ extern "C" {
 int rge_abi_version(void) { return RGE_ABI_VERSION; }
 const char* rge_last_error(void) { return g_err; }
 int64_t rge_launch_count(void) { return g_launches.load(); }
+
+int rge_profile_enable(int32_t on) {
+  g_prof = on != 0;
+  return RGE_OK;
+}
+
+int rge_profile_collect(double* ms, double* work, int64_t* count) {
+  if (!ms || !work || !count) return fail(RGE_ERR_INVALID, "rge_profile_collect: null argument");
+  RGE_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < PC_NCLS; ++c) { ms[c] = 0; work[c] = 0; count[c] = 0; }
+  for (const ProfRec& r : g_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; work[r.cls] += r.work; count[r.cls] += 1; }
+    g_pool.push_back(r.a);
+    g_pool.push_back(r.b);
+  }
+  g_recs.clear();
+  return RGE_OK;
+}
 
 int rge_op_gemm(const rge_gemm_desc* d, void* stream) {
   if (!d || !d->A || !d->W || !d->out) return fail(RGE_ERR_INVALID, "rge_op_gemm: null operand");
@@ -194,6 +235,7 @@ int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, 
   a.gate = gate; a.res = res; a.ldr = ldr; a.norm_w = norm_w; a.rope_cs = rope; a.rope_map = rope_map;
   a.rope_off = rope_off;
   if (M <= 0) return RGE_OK;
+  ProfScope prof(st, PC_GEMM, 2.0 * M * (double)N * K);
   RGE_LAUNCH(launch_gemm(a, h->num_sms, st));
   return RGE_OK;
 }
@@ -453,7 +495,10 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
     AttnArgs at;
     at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
     at.Sq = MA; at.Skv = S; at.H = h->H;
-    RGE_LAUNCH(launch_attention(at, st));
+    {
+      ProfScope prof(st, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H);
+      RGE_LAUNCH(launch_attention(at, st));
+    }
     // out projections with gate * (.) + residual fused
     RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
                  nullptr, 0, 0, g_msa, x_img, D));
@@ -488,7 +533,10 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
     AttnArgs at;
     at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
     at.Sq = MA; at.Skv = S; at.H = h->H;
-    RGE_LAUNCH(launch_attention(at, st));
+    {
+      ProfScope prof(st, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H);
+      RGE_LAUNCH(launch_attention(at, st));
+    }
     RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
                  nullptr, 0, 0, g, h->h, D));
   }

@@ -31,6 +31,27 @@ def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shif
     return base_shift + slope * (image_seq_len - base_seq_len)
 
 
+_MASK_ALLGATHER = False
+
+
+def enable_mask_allgather(on: bool = True) -> None:
+    """Multi-GPU (one image stream per rank): after the partition kernel every rank all-gathers the raw
+    mask bytes over NCCL so each holds the [world, L] batch mask (`MANAGER.batch_masks`); the only collective on the
+    path. Requires torch.distributed to be initialised with the nccl backend (gloo in the CPU tests)."""
+    global _MASK_ALLGATHER
+    _MASK_ALLGATHER = bool(on)
+
+
+def allgather_masks(raw_mask: torch.Tensor):
+    """[L] uint8 per rank -> [world, L] on every rank (no-op without an initialised process group)."""
+    import torch.distributed as dist
+    if not (_MASK_ALLGATHER and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return raw_mask[None]
+    out = torch.empty(dist.get_world_size() * raw_mask.numel(), dtype=raw_mask.dtype, device=raw_mask.device)
+    dist.all_gather_into_tensor(out, raw_mask.contiguous())
+    return out.view(dist.get_world_size(), raw_mask.numel())
+
+
 def _scalar(s: torch.Tensor) -> float:
     """A 0-dim fp32 schedule scalar as the CUDA reference would apply it to a bf16 tensor (params.py)."""
     return float(s.to(torch.bfloat16)) if SCALAR_ROUNDS_TO_BF16 else float(s)
@@ -89,6 +110,10 @@ class RegionESchedulerMixin:
             raw = ops.partition(x, v, M.condition_latent.reshape(-1, ch), _scalar(dt_final), float(M.threshold))
             gh = M.height // (M.patch_size * M.vae_scale_factor)
             gw = M.width // (M.patch_size * M.vae_scale_factor)
+            M.batch_masks = allgather_masks(raw)       # [world, L]; this rank's image is row `rank`
+            if M.batch_masks.shape[0] > 1:
+                import torch.distributed as dist
+                raw = M.batch_masks[dist.get_rank()]
             M.edited_mask, M.edited_ids, M.unedited_ids = ops.compact(raw, gh, gw, bool(M.erosion_dilation))
             prev = ops.euler(x, v, _scalar(dt), _scalar(dt_direct), edited_mask=M.edited_mask)
         elif M.prev_refresh_step is not None and M.current_step == M.prev_refresh_step:          # :665-677
