@@ -176,11 +176,13 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
 int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
                  float timestep_x1000, void* v_out, int32_t n_out, void* stream);
 
-/* Optional timing of the engine's tensor-core launches with CUDA events on the caller's stream (bench.py roofline).
- * rge_profile_collect synchronises the device and returns, per class c (0 = GEMM, 1 = attention): summed kernel
- * milliseconds, summed algorithmic FLOPs (2MNK resp. 4*Sq*Skv*128*H) and the launch count; then clears. */
+/* Optional timing of the engine's tensor-core launches with CUDA events on the streams they run on (bench.py
+ * roofline). rge_profile_collect synchronises the device and returns, per class c (0 = GEMM, 1 = attention):
+ * ms_busy = length of the UNION of the launches' [start, end] intervals (independent GEMMs of one block overlap on the
+ * library's side streams), ms_sum = plain sum of the durations, work = summed algorithmic FLOPs (2MNK resp.
+ * 4*Sq*Skv*128*H), count = launches; then clears. */
 int rge_profile_enable(int32_t on);
-int rge_profile_collect(double* ms, double* work, int64_t* count);
+int rge_profile_collect(double* ms_busy, double* ms_sum, double* work, int64_t* count);
 
 /* Number of kernels this library has launched since creation of the process (bench.py's gpu_launches). */
 int64_t rge_launch_count(void);

@@ -1,10 +1,13 @@
 // C ABI (include/regione_b200.h): kernel-level entry points and the engine that runs one patched transformer
 // forward (RegionE/FluxKontext/inplace.py:413-576 with the attention processor of :694-824) per call.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/regione_b200.h"
@@ -24,6 +27,7 @@ std::atomic<long long> g_launches{0};
 enum { PC_GEMM = 0, PC_ATTN = 1, PC_NCLS = 2 };
 struct ProfRec { int cls; double work; cudaEvent_t a, b; };
 bool g_prof = false;
+cudaEvent_t g_base = nullptr;
 std::vector<ProfRec> g_recs;
 std::vector<cudaEvent_t> g_pool;
 cudaEvent_t prof_event() {
@@ -98,20 +102,48 @@ int64_t rge_launch_count(void) { return g_launches.load(); }
 
 int rge_profile_enable(int32_t on) {
   g_prof = on != 0;
+  if (g_prof) {
+    if (!g_base) RGE_CUDA(cudaEventCreate(&g_base));
+    RGE_CUDA(cudaDeviceSynchronize());
+    RGE_CUDA(cudaEventRecord(g_base, 0));
+    RGE_CUDA(cudaEventSynchronize(g_base));
+  }
   return RGE_OK;
 }
 
-int rge_profile_collect(double* ms, double* work, int64_t* count) {
-  if (!ms || !work || !count) return fail(RGE_ERR_INVALID, "rge_profile_collect: null argument");
+int rge_profile_collect(double* ms_busy, double* ms_sum, double* work, int64_t* count) {
+  if (!ms_busy || !ms_sum || !work || !count) return fail(RGE_ERR_INVALID, "rge_profile_collect: null argument");
   RGE_CUDA(cudaDeviceSynchronize());
-  for (int c = 0; c < PC_NCLS; ++c) { ms[c] = 0; work[c] = 0; count[c] = 0; }
+  std::vector<std::pair<float, float>> iv[PC_NCLS];
+  for (int c = 0; c < PC_NCLS; ++c) { ms_busy[c] = 0; ms_sum[c] = 0; work[c] = 0; count[c] = 0; }
   for (const ProfRec& r : g_recs) {
-    float t = 0.f;
-    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; work[r.cls] += r.work; count[r.cls] += 1; }
+    float t0 = 0.f, t1 = 0.f;
+    if (g_base && cudaEventElapsedTime(&t0, g_base, r.a) == cudaSuccess &&
+        cudaEventElapsedTime(&t1, g_base, r.b) == cudaSuccess) {
+      iv[r.cls].push_back({t0, t1});
+      ms_sum[r.cls] += t1 - t0;
+      work[r.cls] += r.work;
+      count[r.cls] += 1;
+    }
     g_pool.push_back(r.a);
     g_pool.push_back(r.b);
   }
   g_recs.clear();
+  // launches of one class overlap on the side streams: the class is "busy" over the union of its intervals
+  for (int c = 0; c < PC_NCLS; ++c) {
+    std::sort(iv[c].begin(), iv[c].end());
+    float lo = 0.f, hi = -1.f;
+    for (const auto& x : iv[c]) {
+      if (hi < lo || x.first > hi) {
+        if (hi >= lo) ms_busy[c] += hi - lo;
+        lo = x.first;
+        hi = x.second;
+      } else if (x.second > hi) {
+        hi = x.second;
+      }
+    }
+    if (hi >= lo) ms_busy[c] += hi - lo;
+  }
   return RGE_OK;
 }
 
@@ -209,6 +241,11 @@ struct rge_handle {
   GemvJob* jobs = nullptr;                 // [2 + n_mod] step jobs, then per pass 4 image jobs
   int n_mod = 0;
   size_t pass_small_stride = 0;
+  // independent GEMMs of one block run on library-owned side streams so that small-M launches (text stream,
+  // region steps) fill the SMs the persistent grid of a neighbour leaves idle; joined before every attention
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_main = nullptr, ev_aux[3] = {nullptr, nullptr, nullptr};
+  bool fanout = true;
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
@@ -293,6 +330,12 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   A(dalloc(&h->sel_img, S));
   A(dalloc(&h->sel_all, S));
   A(dalloc(&h->jobs, (size_t)2 + h->n_mod + 4 * cfg->n_pass));
+  for (int i = 0; i < 3; ++i) {
+    A(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&h->ev_aux[i], cudaEventDisableTiming));
+  }
+  A(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  if (const char* env = getenv("RGE_NO_FANOUT")) h->fanout = env[0] == '0' || env[0] == 0;
   if (e != cudaSuccess) {
     rge_destroy(h);
     return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));
@@ -311,6 +354,11 @@ int rge_destroy(rge_handle* h) {
                   h->rope, h->ids, h->sel_img, h->sel_all, h->jobs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int i = 0; i < 3; ++i) {
+    if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+    if (h->ev_aux[i]) cudaEventDestroy(h->ev_aux[i]);
+  }
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
   delete h;
   return RGE_OK;
 }
@@ -467,7 +515,25 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
   bf16* big_img = h->big + (size_t)T * ldb;
   const bf16* mod = h->mods;
   int layer = 0;
-  // ---- double-stream blocks
+  // side streams: sT carries the text chain of the double blocks (and the MLP of the single blocks), sK / sV the
+  // K and V projections; `link(from, ev, to)` makes `to` wait for everything enqueued on `from` so far
+  const bool fan = h->fanout;
+  cudaStream_t sT = fan ? h->aux[0] : st, sK = fan ? h->aux[1] : st, sV = fan ? h->aux[2] : st;
+  auto link = [&](cudaStream_t from, cudaEvent_t ev, cudaStream_t to) -> cudaError_t {
+    if (from == to) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(ev, from);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
+  };
+  auto attention = [&](bf16* kc, bf16* vc) -> int {
+    AttnArgs at;
+    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
+    at.Sq = MA; at.Skv = S; at.H = h->H;
+    ProfScope prof(st, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H);
+    RGE_LAUNCH(launch_attention(at, st));
+    return RGE_OK;
+  };
+  // ---- double-stream blocks: image chain on `st`, text chain on sT, joined around attention
+  if (h->cfg.n_double > 0) RGE_CUDA(link(st, h->ev_main, sT));
   for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
     const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
                *g_mlp = mod + 5 * D;
@@ -477,66 +543,66 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
     RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
-    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, st));
+    RGE_CUDA(link(st, h->ev_main, sK));
+    RGE_CUDA(link(st, h->ev_main, sV));
     // image stream q/k/v; k,v rows scattered into the cache at T + sel[m]
     RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr,
                  T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T));
-    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D,
+    RGE_TRY(gemm(h, sK, n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D,
                  h->sel_img, T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T));
-    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T,
+    RGE_TRY(gemm(h, sV, n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T,
                  0));
     // text stream q/k/v (recomputed every step: the reference does not cache text K/V)
-    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D,
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, sT));
+    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D,
                  nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0));
-    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D,
+    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D,
                  nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0));
-    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0,
+    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0,
                  0));
-    AttnArgs at;
-    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
-    at.Sq = MA; at.Skv = S; at.H = h->H;
-    {
-      ProfScope prof(st, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H);
-      RGE_LAUNCH(launch_attention(at, st));
-    }
-    // out projections with gate * (.) + residual fused
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    RGE_CUDA(link(sK, h->ev_aux[1], st));
+    RGE_CUDA(link(sV, h->ev_aux[2], st));
+    RGE_TRY(attention(kc, vc));
+    RGE_CUDA(link(st, h->ev_main, sT));
+    // out projections with gate * (.) + residual fused, then the feed-forward; each stream on its own chain
     RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
                  nullptr, 0, 0, g_msa, x_img, D));
-    RGE_TRY(gemm(h, st, h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h,
+    RGE_TRY(gemm(h, sT, h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h,
                  D, nullptr, 0, 0, cg_msa, h->h, D));
-    // feed-forward, both streams
     RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
-    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, st));
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, sT));
     RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb,
+                 nullptr, 0, D));
+    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb,
                  nullptr, 0, D));
     RGE_TRY(gemm(h, st, big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES,
                  x_img, D, nullptr, 0, 0, g_mlp, x_img, D));
-    RGE_TRY(gemm(h, st, h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb,
-                 nullptr, 0, D));
-    RGE_TRY(gemm(h, st, h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES,
+    RGE_TRY(gemm(h, sT, h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES,
                  h->h, D, nullptr, 0, 0, cg_mlp, h->h, D));
   }
+  if (h->cfg.n_double > 0) RGE_CUDA(link(sT, h->ev_aux[0], st));
   // ---- single-stream blocks on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
   for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
     const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
     RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
+    RGE_CUDA(link(st, h->ev_main, sT));
+    RGE_CUDA(link(st, h->ev_main, sK));
+    RGE_CUDA(link(st, h->ev_main, sV));
+    RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr,
+                 0, D));
     RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
                  0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0));
-    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
+    RGE_TRY(gemm(h, sK, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
                  0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
-    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
+    RGE_TRY(gemm(h, sV, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
                  0));
-    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr,
-                 0, D));
-    AttnArgs at;
-    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
-    at.Sq = MA; at.Skv = S; at.H = h->H;
-    {
-      ProfScope prof(st, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H);
-      RGE_LAUNCH(launch_attention(at, st));
-    }
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    RGE_CUDA(link(sK, h->ev_aux[1], st));
+    RGE_CUDA(link(sV, h->ev_aux[2], st));
+    RGE_TRY(attention(kc, vc));
     RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
                  nullptr, 0, 0, g, h->h, D));
   }

@@ -3,8 +3,9 @@
 // One CTA owns 256 query rows (two 128-row tiles) of one head and streams the whole K/V cache of that head:
 //   warp 0        TMA producer: Q once, then K_j / V_j tiles through a 5-slot shared-memory ring
 //   warp 1        MMA issuer (one thread): S_i = Q_i K_j^T (SS), O_i += P_i V_j (P from TMEM, V MN-major from smem)
-//   warps 2-5     softmax group 0 (query tile 0), one thread per query row
-//   warps 6-9     softmax group 1 (query tile 1)
+//   warps 2-3     idle (pad warpgroup 0 so that setmaxnreg can hand its registers to the softmax warpgroups)
+//   warps 4-7     softmax group 0 (query tile 0), one thread per query row, 208 registers
+//   warps 8-11    softmax group 1 (query tile 1)
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_i (bf16 pairs) overwrites the first 64 columns
 // of S_i once a row's scores are in registers. The two tiles ping-pong so the tensor pipe works on one while the
 // other's softmax runs. Online softmax uses a lazy reference maximum: O is only rescaled (by the softmax group
@@ -21,7 +22,7 @@ namespace rge {
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;
 constexpr int kTile = 128;             // query rows per tile, kv rows per tile, head dim
 constexpr int kHalfBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled half tile
 constexpr int kTileBytes = 2 * kHalfBytes;
@@ -89,6 +90,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // register re-distribution: warpgroup 0 (TMA / MMA / idle) keeps 88, the softmax warpgroups take 208 each
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -170,9 +174,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ------------------------------------------------------------ softmax groups
-    const int grp = (warp - 2) >> 2;  // query tile handled by this warp group
+    const int grp = (warp - 4) >> 2;  // query tile handled by this warp group
     const int qtr = warp & 3;         // TMEM lane quarter this warp may access
     const int row = q0 + grp * kTile + qtr * 32 + lane;
     const uint32_t lane_base = uint32_t(qtr * 32) << 16;
@@ -185,19 +191,28 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mbar_wait(&s_full[grp], j & 1);
       tc_fence_after();
       const int n_valid = min(kTile, p.Skv - j * kTile);
-      // pass 1: row maximum of the raw scores
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
+      // the whole score row in registers: four 32-column TMEM loads in flight, one wait
+      uint32_t v[128];
+      tmem_ld32p(t_s, v);
+      tmem_ld32p(t_s + 32, v + 32);
+      tmem_ld32p(t_s + 64, v + 64);
+      tmem_ld32p(t_s + 96, v + 96);
+      tmem_ld_wait();
+      if (n_valid < kTile) {  // KV tail (last tile only): masked columns behave as -inf
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          float s = __uint_as_float(v[jj]);
-          if (c * 32 + jj < n_valid) mx = fmaxf(mx, s);
-        }
+        for (int jj = 0; jj < 128; ++jj)
+          if (jj >= n_valid) v[jj] = 0xff800000u;
       }
+      // row maximum of the raw scores, four independent chains
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 128; jj += 8) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[jj + 0]), __uint_as_float(v[jj + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[jj + 4]), __uint_as_float(v[jj + 5])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[jj + 6]), __uint_as_float(v[jj + 7])));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       if (j == 0) {
         m_run = mx;
       } else {
@@ -210,12 +225,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           const float alpha = ex2((m_run - m_new) * sl2);
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_o + c * 32, v);
+            uint32_t o[32];
+            tmem_ld32(t_o + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) * alpha);
-            tmem_st32(t_o + c * 32, v);
+            for (int jj = 0; jj < 32; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
+            tmem_st32(t_o + c * 32, o);
           }
           tmem_st_wait();
           l_run *= alpha;
@@ -224,23 +239,20 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
       // pass 2: P = exp2((s - m) * scale * log2 e), packed bf16 pairs into the first 64 columns of S_i
       const float neg_m = -m_run * sl2;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(v[jj]), sl2, neg_m));
-          float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
-          if (c * 32 + jj >= n_valid) p0 = 0.f;
-          if (c * 32 + jj + 1 >= n_valid) p1 = 0.f;
-          l_run += p0 + p1;
-          pk[jj >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(t_s + c * 16, pk);
+      for (int jj = 0; jj < 128; jj += 4) {
+        const float p0 = ex2(fmaf(__uint_as_float(v[jj + 0]), sl2, neg_m));
+        const float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
+        const float p2 = ex2(fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m));
+        const float p3 = ex2(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
+        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+        v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
+        v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
       }
+      l_run += (sum0 + sum1) + (sum2 + sum3);
+      tmem_st32p(t_s, v);
+      tmem_st32p(t_s + 32, v + 32);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -9,7 +9,10 @@
 // (RegionE/FluxKontext/fused_kernels.py:9-101): the scatter is the `row_map` of the epilogue, and the
 // per-head RMSNorm + RoPE the reference re-applies to the whole cache every step
 // (RegionE/FluxKontext/inplace.py:756-763, 792-794) is fused here so the cache holds post-norm/post-RoPE rows.
+#include <cstdlib>
+
 #include "gemm.cuh"
+#include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -30,22 +33,6 @@ struct Cfg {
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
   static constexpr int kTmemCols = 2 * BN;
-};
-
-struct GemmDev {
-  int M, N, K;
-  const __nv_bfloat16* bias;
-  __nv_bfloat16* out;
-  long ldo;
-  const int* row_map;
-  int row_off, col_off;
-  const __nv_bfloat16* gate;
-  const __nv_bfloat16* res;
-  long ldr;
-  const __nv_bfloat16* norm_w;
-  const float2* rope_cs;
-  const int* rope_map;
-  int rope_off;
 };
 
 __device__ __forceinline__ float ldg_bf16(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
@@ -306,6 +293,16 @@ cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   if (a.epilogue == EPI_NORM_ROPE && (a.N % 128)) return cudaErrorInvalidValue;
   if (a.epilogue == EPI_GATE_RES && (!a.gate || !a.res || (a.ldr % 8))) return cudaErrorInvalidValue;
+  // large-M launches (FULL steps) go to the CTA-pair kernel; RGE_2CTA_MIN_M=0 disables it
+  static int min_m_2cta = -1;
+  if (min_m_2cta < 0) {
+    const char* env = getenv("RGE_2CTA_MIN_M");
+    min_m_2cta = env ? atoi(env) : 2048;
+  }
+  if (min_m_2cta > 0 && a.M >= min_m_2cta && a.N % 256 == 0) {
+    cudaError_t e = launch_gemm_2cta(a, num_sms, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
   if (a.N % 256 == 0) return launch_bn<256>(a, num_sms, stream);
   return launch_bn<128>(a, num_sms, stream);
 }

@@ -1,0 +1,177 @@
+// 2-CTA (cluster of two, tcgen05 cta_group::2) variant of the persistent bf16 GEMM for the large-M launches of a FULL
+// step: one 256 x 256 output tile per CTA pair. Each CTA stages its own 128 rows of A and its own 128 rows (half of
+// N) of W, the leader CTA's single MMA thread issues M=256 N=256 K=16 instructions that read both halves, and each
+// CTA's TMEM receives the 128 x 256 accumulator of its M half. Compared with the 1-CTA kernel this halves the
+// shared-memory operand traffic per FLOP and leaves room for a 6-stage ring (32 KB per stage per CTA).
+//
+//   warp 0      TMA producer (both CTAs; transaction bytes are credited to the leader's `full` barrier)
+//   warp 1      MMA issuer   (leader CTA only) / TMEM allocation (both CTAs, cta_group::2)
+//   warps 2-5   epilogue     (both CTAs, shared with gemm.cu through gemm_epilogue.cuh)
+#include "gemm_epilogue.cuh"
+#include "tmap.cuh"
+
+namespace rge {
+
+namespace {
+
+constexpr int BM = 128;   // rows per CTA (256 per pair)
+constexpr int BN = 256;   // columns per pair (128 rows of W staged per CTA)
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kStages = 6;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kBBytes = (BN / 2) * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+constexpr int kTmemCols = 512;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);    // one arrive per CTA's producer; bytes of all four TMA loads
+      mbar_init(&empty_bar[i], 1);   // multicast tcgen05.commit from the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);   // multicast tcgen05.commit from the leader
+      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
+          tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t use = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], use ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t a_desc = make_sdesc_sw128(sa, 0, 1024);
+          const uint64_t b_desc = make_sdesc_sw128(sb, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          tc_commit_pair(&empty_bar[stage], 3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(&tfull_bar[acc], 3);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (both CTAs)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int acc = it & 1;
+      const uint32_t use = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], use);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      gemm_epilogue_row<BN, EPI>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
+template <int EPI>
+cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap map_a, map_b;
+  if (!make_tmap_bf16_2d(&map_a, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, BN / 2)) return cudaErrorInvalidValue;
+  const GemmDev p = to_dev(a);
+  const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + BN - 1) / BN);
+  const int max_pairs = num_sms / 2;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  gemm2_kernel<EPI><<<2 * pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gemm_2cta(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.N % BN) return cudaErrorNotSupported;
+  switch (a.epilogue) {
+    case EPI_STORE: return launch_t<EPI_STORE>(a, num_sms, stream);
+    case EPI_GELU: return launch_t<EPI_GELU>(a, num_sms, stream);
+    case EPI_GATE_RES: return launch_t<EPI_GATE_RES>(a, num_sms, stream);
+    case EPI_NORM_ROPE: return launch_t<EPI_NORM_ROPE>(a, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace rge

@@ -39,6 +39,41 @@ def test_gemm_store_matches_linear(M, N, K):
     assert rel_l2(y2, a.float() @ w.float().t()) <= BF16_TOL
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 256, 64), (2049, 512, 192), (4000, 3072, 256), (2304, 768, 3072)])
+def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
+    """M >= 2048 and N % 256 == 0 dispatch to the cta_group::2 kernel (gemm2.cu): ragged M (second CTA partly or
+    fully out of range), every epilogue, scatter."""
+    from regione_b200 import _lib, ops
+    g = _gen(21)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    lin = F.linear(a, w, b)
+    assert rel_l2(ops.gemm(a, w, b), a.float() @ w.float().t() + b.float()) <= BF16_TOL
+    assert rel_l2(ops.gemm(a, w, b, epilogue=_lib.EPI_GELU), F.gelu(lin, approximate="tanh")) <= BF16_TOL
+    gate = torch.randn(N, device="cuda", generator=g).bfloat16()
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = res.clone()
+    ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, gate=gate, res=out, out=out)
+    assert rel_l2(out, res + gate[None] * lin) <= BF16_TOL
+    S = M + 100
+    rows = torch.randperm(S, device="cuda", generator=g)[:M]
+    cache = torch.zeros(S, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, b, out=cache, row_map=rows.int())
+    assert rel_l2(cache[rows], lin) <= BF16_TOL
+    if N % 128 == 0:
+        H = N // 128
+        nw = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
+        ids = torch.zeros(S, 3, device="cuda")
+        ids[:, 1] = torch.arange(S, device="cuda") // 64
+        ids[:, 2] = torch.arange(S, device="cuda") % 64
+        cs = ops.rope_table(ids)
+        cos, sin = of.rope_cos_sin(ids)
+        q = ops.gemm(a, w, b, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=rows.int())
+        x = of.apply_rope(of.rms_norm(lin.view(1, M, H, 128).transpose(1, 2), nw), (cos[rows], sin[rows]))
+        assert rel_l2(q, x.transpose(1, 2).reshape(M, N)) <= BF16_TOL
+
+
 def test_gemm_fused_epilogues():
     from regione_b200 import _lib, ops
     g = _gen(2)
