@@ -591,18 +591,20 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
     RGE_CUDA(link(st, h->ev_main, sT));
     RGE_CUDA(link(st, h->ev_main, sK));
     RGE_CUDA(link(st, h->ev_main, sV));
-    RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr,
-                 0, D));
     RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
                  0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0));
     RGE_TRY(gemm(h, sK, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
                  0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
     RGE_TRY(gemm(h, sV, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
                  0));
-    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr,
+                 0, D));
     RGE_CUDA(link(sK, h->ev_aux[1], st));
     RGE_CUDA(link(sV, h->ev_aux[2], st));
     RGE_TRY(attention(kc, vc));
+    // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT: its CTAs and
+    // the attention CTAs share the SMs, which fills the partial last wave of either kernel
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
     RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
                  nullptr, 0, 0, g, h->h, D));
   }

@@ -43,6 +43,23 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], relative error 7.5e-5,
+// far below the bf16 rounding of P): used for one score in four so that the MUFU pipe, which is co-critical with the
+// tensor pipe in this kernel (16 ex2 per clock per SM), is not the only source of exponentials.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;                 // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
+  const float f = x - (r - 12582912.0f);           // fraction in [-0.5, 0.5]
+  float p = fmaf(0.055171459913253784f, f, 0.2426108568906784f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+#ifndef RGE_ATTN_POLY_EX2
+#define RGE_ATTN_POLY_EX2 1
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnDev p) {
@@ -245,7 +262,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const float p0 = ex2(fmaf(__uint_as_float(v[jj + 0]), sl2, neg_m));
         const float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
         const float p2 = ex2(fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m));
+#if RGE_ATTN_POLY_EX2
+        const float p3 = ex2_poly(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
+#else
         const float p3 = ex2(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
+#endif
         sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
         v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
         v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
