@@ -72,8 +72,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + kSlots;
   uint64_t* s_full = kv_empty + kSlots;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_bar = p_full + 2;
+  uint64_t* p_half = s_full + 2;   // [group][half]: P columns [64 half, 64 half + 64) of the group are in TMEM
+  uint64_t* o_bar = p_half + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -93,7 +93,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_half[2 * i], 4);
+      mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&o_bar[i], 1);
     }
     fence_mbar_init();
@@ -152,11 +153,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       };
       // O_i += P_i V : contraction over kv, 8 steps of 16 rows (2048 B); V is [kv][d] = MN-major B with two
       // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO)
-      auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate) {
+      // issued in two halves of 64 kv rows: the first starts while the softmax group still exponentiates the second
+      auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate, int j) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8,
-                  make_sdesc_sw128(v_addr + kk * 2048, kHalfBytes, 1024), idesc_pv, accumulate || kk != 0);
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&p_half[2 * i + half], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 4 * half; kk < 4 * half + 4; ++kk) {
+            umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8,
+                    make_sdesc_sw128(v_addr + kk * 2048, kHalfBytes, 1024), idesc_pv, accumulate || kk != 0);
+          }
         }
       };
       mbar_wait(q_full, 0);
@@ -170,18 +177,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int tv = 2 * j + 1, tk = 2 * j + 2;
         const bool more = j + 1 < n_tiles;
         wait_kv(tv);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, slot_addr(tv), j > 0);
+        issue_pv(0, slot_addr(tv), j > 0, j);
         tc_commit(&o_bar[0]);
         if (more) {
           wait_kv(tk);
           issue_qk(0, slot_addr(tk));
           tc_commit(&s_full[0]);
         }
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, slot_addr(tv), j > 0);
+        issue_pv(1, slot_addr(tv), j > 0, j);
         tc_commit(&o_bar[1]);
         tc_commit(&kv_empty[tv % kSlots]);
         if (more) {
@@ -258,26 +261,29 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const float neg_m = -m_run * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < 128; jj += 4) {
-        const float p0 = ex2(fmaf(__uint_as_float(v[jj + 0]), sl2, neg_m));
-        const float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
-        const float p2 = ex2(fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m));
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int jj = 64 * half; jj < 64 * half + 64; jj += 4) {
+          const float p0 = ex2(fmaf(__uint_as_float(v[jj + 0]), sl2, neg_m));
+          const float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
+          const float p2 = ex2(fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m));
 #if RGE_ATTN_POLY_EX2
-        const float p3 = ex2_poly(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
+          const float p3 = ex2_poly(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
 #else
-        const float p3 = ex2(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
+          const float p3 = ex2(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
 #endif
-        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
-        v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
-        v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
+          sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+          v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
+          v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+        // publish this half of P (32 TMEM columns = 64 kv positions) so its PV MMAs can start
+        tmem_st32p(t_s + 32 * half, v + 32 * half);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_half[2 * grp + half]);
       }
       l_run += (sum0 + sum1) + (sum2 + sum3);
-      tmem_st32p(t_s, v);
-      tmem_st32p(t_s + 32, v + 32);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[grp]);
     }
     // epilogue: O_i / l -> bf16 -> global
     mbar_wait(&o_bar[grp], (n_tiles - 1) & 1);

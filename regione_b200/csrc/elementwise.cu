@@ -82,6 +82,60 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
   }
 }
 
+// Same operation with the row held in registers (one global read): D = 256 * NV.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_modulate_reg_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
+                                                              const __nv_bfloat16* __restrict__ scale,
+                                                              const __nv_bfloat16* __restrict__ shift,
+                                                              __nv_bfloat16* __restrict__ out, long ldo, int M) {
+  constexpr int D = 256 * NV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long)m * ldx);
+  uint4 r[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r[i] = xr[lane + 32 * i];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(r[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(r[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = f[j] - mean;
+      q += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-6f);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale);
+  const uint4* sh = reinterpret_cast<const uint4*>(shift);
+  uint4* o = reinterpret_cast<uint4*>(out + (long)m * ldo);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8], a[8], b[8];
+    unpack8(r[i], f);
+    unpack8(__ldg(sc + lane + 32 * i), a);
+    unpack8(__ldg(sh + lane + 32 * i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float n = bf16_round((f[j] - mean) * rstd);
+      const float t = bf16_round(n * bf16_round(1.0f + a[j]));
+      f[j] = t + b[j];
+    }
+    o[lane + 32 * i] = pack8(f);
+  }
+}
+
 // ------------------------------------------------------------------ batched GEMV
 __global__ void __launch_bounds__(256) gemv_batch_kernel(const GemvJob* __restrict__ jobs) {
   extern __shared__ float xs[];
@@ -316,7 +370,9 @@ cudaError_t launch_ln_modulate(const __nv_bfloat16* x, long ldx, const __nv_bflo
                                cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
   if (D % 8 || ldx % 8 || ldo % 8) return cudaErrorInvalidValue;
-  ln_modulate_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M, D);
+  if (D == 3072) ln_modulate_reg_kernel<12><<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
+  else if (D == 256) ln_modulate_reg_kernel<1><<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
+  else ln_modulate_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M, D);
   return cudaGetLastError();
 }
 

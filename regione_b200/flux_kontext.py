@@ -267,8 +267,12 @@ class RegionEFluxKontextPipelineMixin:
         cache = None
         record = bool(getattr(self, "regione_record", False))   # tests: keep per-step tensors
         self.regione_trace = {"modes": [], "latents": [], "noise_pred": []}
+        marks = [] if getattr(self, "regione_time_steps", False) else None   # diagnostics: CUDA event per step
         for i in range(N):
             assert i == M.current_step                                                            # :293
+            if marks is not None:
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
             t = ts_host[i]
             skip, ratio = plan[i]
             if skip:                                                                              # :315-318
@@ -294,6 +298,11 @@ class RegionEFluxKontextPipelineMixin:
             if record:
                 self.regione_trace["latents"].append(x.clone())
                 self.regione_trace["noise_pred"].append(cache.clone())
+        if marks is not None:
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
+            marks[-1].synchronize()
+            self.regione_trace["step_ms"] = [a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:])]
         self.regione_trace["edited_ids"] = M.edited_ids
         self.regione_trace["unedited_ids"] = M.unedited_ids
         return x[None]
