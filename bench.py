@@ -157,7 +157,9 @@ def run_ours(args):
     txt = 32 if args.arch == "tiny" else TXT
     pipe = syn.build_pipeline(arch, seed=110, device=dev)
     helper = RegionEHelper(pipe)
-    helper.set_params(**PARAMS)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):   # the helper prints its parameters (RegionE.py:51); keep stdout = JSON
+        helper.set_params(**PARAMS)
     helper.enable()
     pipe = helper.pipeline
     host = syn.make_inputs(110 + rank, grid, grid, txt, arch["ctx_dim"], arch["pooled_dim"], rho=args.rho)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RGE_ABI_VERSION 1
+#define RGE_ABI_VERSION 2
 
 enum rge_status {
   RGE_OK = 0,
@@ -73,6 +73,15 @@ int rge_op_attention(const rge_attn_desc* d, void* stream);
 int rge_op_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, void* out, int64_t ldo,
                        int32_t M, int32_t D, void* stream);
 
+/* out = RMSNorm(x) * weight over the last dimension (diffusers RMSNorm; Qwen txt_norm, QwenImageEdit/inplace.py:518). */
+int rge_op_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo, int32_t M, int32_t D,
+                   float eps, void* stream);
+
+/* Norm-rescaled classifier-free guidance (QwenImageEdit/inplace.py:386-405): comb = neg + scale * (pos - neg);
+ * out = comb * (||pos|| / ||comb||) per token; pos, neg, out: [M, channels]. */
+int rge_cfg_rescale(const void* pos, const void* neg, float scale, void* out, int32_t M, int32_t channels,
+                    void* stream);
+
 /* Rotary table of FluxPosEmbed(theta 10000, axes (16,56,56)): ids fp32 [S,3] -> cs fp32 [S,64,2] = (cos, sin). */
 int rge_op_rope_table(const float* ids, float* cs, int32_t S, void* stream);
 
@@ -119,6 +128,12 @@ typedef struct rge_config {
   int32_t guidance_embeds;
   int32_t n_pass;         /* independent text/KV-cache sets (1; 2 for CFG pairs) */
   int32_t device;
+  int32_t external_embed; /* bit 0: rotary table and embedded context come from the family's own pos_embed / text
+                             front end through rge_begin_image_ex (Qwen: txt_norm + txt_in + pos_embed; Step1X:
+                             connector + context_embedder); RGE_G_CTX_EMBED_* stay unset.
+                             bit 1: temb is computed by the family's own modules and handed to rge_dit_step_ex
+                             (Step1X: time_embed + vec_embed); RGE_G_TIME1..POOL2 stay unset.
+                             pooled_dim = 0 drops the pooled-text term of temb (Qwen). */
 } rge_config;
 
 enum rge_block_kind { RGE_BLK_GLOBAL = 0, RGE_BLK_DOUBLE = 1, RGE_BLK_SINGLE = 2 };
@@ -175,6 +190,16 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
  * reference's "write cache at warmup-1 / refresh" modes (inplace.py:717-725). */
 int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
                  float timestep_x1000, void* v_out, int32_t n_out, void* stream);
+
+/* Variants for families whose front end is not FLUX's (rge_config.external_embed = 1).
+ *   rope_cs       fp32 [T+L+C, 64, 2] (cos, sin) per rotary pair for the FULL key sequence, text rows first — what
+ *                 the pipeline's pos_embed returns (Qwen: QwenImageEdit/inplace.py:530-531, 851-855)
+ *   ctx_embedded  [T, dim] text tokens after the family's own context embedding (may be NULL in begin and supplied per
+ *                 step instead: Step1X's connector depends on the timestep, Step1XEdit/inplace.py:514-520)
+ *   temb          [dim] conditioning vector the adaLN modulations are computed from */
+int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const void* ctx_embedded, void* stream);
+int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
+                    const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out, void* stream);
 
 /* Optional timing of the engine's tensor-core launches with CUDA events on the streams they run on (bench.py
  * roofline). rge_profile_collect synchronises the device and returns, per class c (0 = GEMM, 1 = attention):

@@ -73,7 +73,7 @@ class AttnDesc(C.Structure):
 class Config(C.Structure):
     _fields_ = [(n, c_int32) for n in (
         "dim", "heads", "n_double", "n_single", "mlp_ratio", "in_channels", "ctx_dim", "pooled_dim",
-        "txt_len", "lat_len", "cond_len", "guidance_embeds", "n_pass", "device")]
+        "txt_len", "lat_len", "cond_len", "guidance_embeds", "n_pass", "device", "external_embed")]
 
 
 # name -> (restype, argtypes); every name here must be declared in include/regione_b200.h (tests check both ways)
@@ -88,6 +88,8 @@ PROTOTYPES = {
     "rge_op_attention": (c_int32, [C.POINTER(AttnDesc), c_void_p]),
     "rge_op_ln_modulate": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_void_p]),
+    "rge_op_rmsnorm": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
+    "rge_cfg_rescale": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p]),
     "rge_op_rope_table": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p]),
     "rge_gather_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "rge_scatter_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
@@ -102,6 +104,9 @@ PROTOTYPES = {
     "rge_set_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "rge_finalize_weights": (c_int32, [c_void_p]),
     "rge_begin_image": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "rge_begin_image_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "rge_dit_step_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int32, c_void_p]),
     "rge_dit_step": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_float, c_void_p, c_int32,
                                c_void_p]),
 }
@@ -133,7 +138,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rge_abi_version() != 1:
+    if lib.rge_abi_version() != 2:
         raise RegionEB200Error("regione_b200: ABI version mismatch")
     _LIB = lib
     return lib

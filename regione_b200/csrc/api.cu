@@ -177,6 +177,22 @@ int rge_op_ln_modulate(const void* x, int64_t ldx, const void* scale, const void
   return RGE_OK;
 }
 
+int rge_op_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo, int32_t M, int32_t D,
+                   float eps, void* stream) {
+  if (!x || !weight || !out) return fail(RGE_ERR_INVALID, "rge_op_rmsnorm: null operand");
+  RGE_LAUNCH(launch_rmsnorm((const bf16*)x, ldx, (const bf16*)weight, (bf16*)out, ldo, M, D, eps,
+                            (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_cfg_rescale(const void* pos, const void* neg, float scale, void* out, int32_t M, int32_t channels,
+                    void* stream) {
+  if (M > 0 && (!pos || !neg || !out)) return fail(RGE_ERR_INVALID, "rge_cfg_rescale: null operand");
+  RGE_LAUNCH(launch_cfg_rescale((const bf16*)pos, (const bf16*)neg, scale, (bf16*)out, M, channels,
+                                (cudaStream_t)stream));
+  return RGE_OK;
+}
+
 int rge_op_rope_table(const float* ids, float* cs, int32_t S, void* stream) {
   if (!ids || !cs) return fail(RGE_ERR_INVALID, "rge_op_rope_table: null operand");
   RGE_LAUNCH(launch_rope_table(ids, (float2*)cs, S, (cudaStream_t)stream));
@@ -293,7 +309,7 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
     return fail(RGE_ERR_UNSUPPORTED, "rge_create: head_dim must be 128 (dim %d heads %d)", cfg->dim, cfg->heads);
   if (cfg->dim > 4096 || cfg->pooled_dim > 4096 || cfg->dim % 256)
     return fail(RGE_ERR_UNSUPPORTED, "rge_create: dim must be a multiple of 256 and <= 4096");
-  if (cfg->in_channels % 32 || cfg->ctx_dim % 8 || cfg->pooled_dim % 8 || cfg->txt_len < 0 || cfg->lat_len <= 0 ||
+  if (cfg->in_channels % 32 || cfg->ctx_dim % 8 || cfg->pooled_dim % 8 || cfg->pooled_dim < 0 || cfg->ctx_dim < 0 || cfg->txt_len < 0 || cfg->lat_len <= 0 ||
       cfg->cond_len < 0 || cfg->n_pass < 1 || cfg->mlp_ratio < 1 || cfg->n_double < 0 || cfg->n_single < 0)
     return fail(RGE_ERR_INVALID, "rge_create: bad shape");
   RGE_CUDA(cudaSetDevice(cfg->device));
@@ -387,7 +403,12 @@ int rge_finalize_weights(rge_handle* h) {
   if (!h) return fail(RGE_ERR_INVALID, "rge_finalize_weights: null handle");
   for (int s = 0; s < RGE_G_NUM_SLOTS; ++s) {
     const bool guid = s >= RGE_G_GUID1_W && s <= RGE_G_GUID2_B;
-    if (!h->gw[s] && !(guid && !h->cfg.guidance_embeds))
+    const bool ctxs = s == RGE_G_CTX_EMBED_W || s == RGE_G_CTX_EMBED_B;
+    const bool pool = s >= RGE_G_POOL1_W && s <= RGE_G_POOL2_B;
+    const bool tims = s >= RGE_G_TIME1_W && s <= RGE_G_POOL2_B;         // time / guidance / pooled MLPs
+    const bool optional = (guid && !h->cfg.guidance_embeds) || (ctxs && (h->cfg.external_embed & 1)) ||
+                          (pool && h->cfg.pooled_dim == 0) || (tims && (h->cfg.external_embed & 2));
+    if (!h->gw[s] && !optional)
       return fail(RGE_ERR_STATE, "rge_finalize_weights: global slot %d not set", s);
   }
   for (size_t i = 0; i < h->dw.size(); ++i)
@@ -422,7 +443,8 @@ int rge_finalize_weights(rge_handle* h) {
   }
   jobs[j++] = GemvJob{h->G(RGE_G_NORM_OUT_W), h->G(RGE_G_NORM_OUT_B), temb, m, 2 * D, D, 1, 0};
   // per pass: guidance_embedder and text_embedder (pooled) MLPs, evaluated once per image
-  for (int p = 0; p < h->cfg.n_pass; ++p) {
+  const bool has_image_jobs = !(h->cfg.external_embed & 2) && (h->cfg.guidance_embeds || h->cfg.pooled_dim > 0);
+  for (int p = 0; p < h->cfg.n_pass && has_image_jobs; ++p) {
     bf16* gproj = h->ps(p);
     bf16* g1 = gproj + 256;
     bf16* gemb = g1 + D;
@@ -452,6 +474,8 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
   if (h->T > 0 && !txt_ids) return fail(RGE_ERR_INVALID, "rge_begin_image: null txt_ids");
   if (!h->finalized) return fail(RGE_ERR_STATE, "rge_begin_image: weights not finalized");
   if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_begin_image: bad pass %d", pass);
+  if (h->cfg.external_embed) return fail(RGE_ERR_STATE, "rge_begin_image: handle uses rge_begin_image_ex");
+  if (h->cfg.pooled_dim == 0) return fail(RGE_ERR_UNSUPPORTED, "rge_begin_image: pooled_dim 0 needs external_embed");
   cudaStream_t st = (cudaStream_t)stream;
   const int D = h->D, T = h->T;
   // key-side rotary table over the FULL sequence (MANAGER.image_rotary_emb, inplace.py:499); query rows are
@@ -475,8 +499,9 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
   return RGE_OK;
 }
 
-int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
-                 float timestep_x1000, void* v_out, int32_t n_out, void* stream) {
+static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
+                         float timestep_x1000, const void* ext_temb, const void* ext_ctx, void* v_out, int32_t n_out,
+                         void* stream) {
   if (!h || (n_out > 0 && !v_out) || (n_img > 0 && !x_in)) return fail(RGE_ERR_INVALID, "rge_dit_step: null argument");
   if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_dit_step: bad pass %d", pass);
   if (!h->finalized || !h->begun[pass]) return fail(RGE_ERR_STATE, "rge_dit_step: rge_begin_image not called");
@@ -495,18 +520,25 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
   const bf16* pemb = h->ps(pass) + 256 + 2 * D + h->cfg.pooled_dim + D;
 
   RGE_LAUNCH(launch_build_selection(sel, M, T, h->sel_img, h->sel_all, st));
-  // ---- temb = timestep_embedder(proj(t)) [+ guidance_embedder(..)] + text_embedder(pooled)
-  RGE_LAUNCH(launch_timestep_proj(timestep_x1000, tproj, st));
-  RGE_LAUNCH(launch_gemv_batch(h->jobs, 1, D, st));
-  RGE_LAUNCH(launch_gemv_batch(h->jobs + 1, 1, D, st));
-  if (h->cfg.guidance_embeds) RGE_LAUNCH(launch_add3(t2, gemb, pemb, temb, D, st));
-  else RGE_LAUNCH(launch_add3(t2, pemb, nullptr, temb, D, st));
+  if (ext_temb) {
+    // the family's own time/text embedding modules produced temb (Step1X connector/vec_embed, Qwen time_text_embed)
+    RGE_CUDA(cudaMemcpyAsync(temb, ext_temb, (size_t)D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  } else {
+    // ---- temb = timestep_embedder(proj(t)) [+ guidance_embedder(..)] + text_embedder(pooled)
+    RGE_LAUNCH(launch_timestep_proj(timestep_x1000, tproj, st));
+    RGE_LAUNCH(launch_gemv_batch(h->jobs, 1, D, st));
+    RGE_LAUNCH(launch_gemv_batch(h->jobs + 1, 1, D, st));
+    if (h->cfg.guidance_embeds && h->cfg.pooled_dim > 0) RGE_LAUNCH(launch_add3(t2, gemb, pemb, temb, D, st));
+    else if (h->cfg.pooled_dim > 0) RGE_LAUNCH(launch_add3(t2, pemb, nullptr, temb, D, st));
+    else if (h->cfg.guidance_embeds) RGE_LAUNCH(launch_add3(t2, gemb, nullptr, temb, D, st));
+    else RGE_CUDA(cudaMemcpyAsync(temb, t2, (size_t)D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  }
   // ---- adaLN modulation vectors of all blocks
   RGE_LAUNCH(launch_gemv_batch(h->jobs + 2, h->n_mod, 6 * D, st));
   // ---- token embedding: text rows [0,T) come from the per-image context embedding, image rows from x_embedder
   if (T > 0)
-    RGE_CUDA(cudaMemcpyAsync(h->h, h->ctx + (size_t)pass * T * D, (size_t)T * D * sizeof(bf16),
-                             cudaMemcpyDeviceToDevice, st));
+    RGE_CUDA(cudaMemcpyAsync(h->h, ext_ctx ? (const bf16*)ext_ctx : h->ctx + (size_t)pass * T * D,
+                             (size_t)T * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
   RGE_TRY(gemm(h, st, (const bf16*)x_in, h->cfg.in_channels, M, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
                h->G(RGE_G_X_EMBED_B), D, EPI_STORE, h->h, D, nullptr, T, 0));
 
@@ -612,6 +644,35 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
   RGE_LAUNCH(launch_ln_modulate(x_img, D, mod, mod + D, n_img_p, D, n_out, D, st));
   RGE_TRY(gemm(h, st, n_img_p, D, n_out, D, h->G(RGE_G_PROJ_OUT_W), h->G(RGE_G_PROJ_OUT_B), h->cfg.in_channels,
                EPI_STORE, (bf16*)v_out, h->cfg.in_channels, nullptr, 0, 0));
+  return RGE_OK;
+}
+
+int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
+                 float timestep_x1000, void* v_out, int32_t n_out, void* stream) {
+  if (h && (h->cfg.external_embed & 2)) return fail(RGE_ERR_STATE, "rge_dit_step: handle uses rge_dit_step_ex");
+  return dit_step_impl(h, pass, x_in, n_img, sel, timestep_x1000, nullptr, nullptr, v_out, n_out, stream);
+}
+
+int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
+                    const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out, void* stream) {
+  if (!temb) return fail(RGE_ERR_INVALID, "rge_dit_step_ex: null temb");
+  return dit_step_impl(h, pass, x_in, n_img, sel, 0.f, temb, ctx_embedded, v_out, n_out, stream);
+}
+
+int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const void* ctx_embedded, void* stream) {
+  if (!h || !rope_cs) return fail(RGE_ERR_INVALID, "rge_begin_image_ex: null argument");
+  if (!h->finalized) return fail(RGE_ERR_STATE, "rge_begin_image_ex: weights not finalized");
+  if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_begin_image_ex: bad pass %d", pass);
+  if (!(h->cfg.external_embed & 1)) return fail(RGE_ERR_STATE, "rge_begin_image_ex: handle uses rge_begin_image");
+  if (!(h->cfg.external_embed & 2) && (h->cfg.guidance_embeds || h->cfg.pooled_dim > 0))
+    return fail(RGE_ERR_UNSUPPORTED, "rge_begin_image_ex: guidance / pooled embeddings need an external temb");
+  cudaStream_t st = (cudaStream_t)stream;
+  RGE_CUDA(cudaMemcpyAsync(h->rope + (size_t)pass * h->S * 64, rope_cs, (size_t)h->S * 64 * sizeof(float2),
+                           cudaMemcpyDeviceToDevice, st));
+  if (ctx_embedded && h->T > 0)
+    RGE_CUDA(cudaMemcpyAsync(h->ctx + (size_t)pass * h->T * h->D, ctx_embedded,
+                             (size_t)h->T * h->D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+  h->begun[pass] = 1;
   return RGE_OK;
 }
 

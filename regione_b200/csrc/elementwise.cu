@@ -361,6 +361,70 @@ __global__ void __launch_bounds__(1024) morph_compact_kernel(const uint8_t* __re
   }
 }
 
+// ------------------------------------------------------------------ row RMSNorm with weight (Qwen txt_norm)
+// diffusers RMSNorm: fp32 variance, x * rsqrt(var + eps) in fp32, cast to the weight dtype, times weight.
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
+                                                      const __nv_bfloat16* __restrict__ w,
+                                                      __nv_bfloat16* __restrict__ out, long ldo, int M, int D,
+                                                      float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long)m * ldx);
+  const int nv = D >> 3;
+  float q = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(xr[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += f[j] * f[j];
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* o = reinterpret_cast<uint4*>(out + (long)m * ldo);
+  for (int i = lane; i < nv; i += 32) {
+    float f[8], a[8];
+    unpack8(xr[i], f);
+    unpack8(__ldg(wr + i), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] * rstd) * a[j];
+    o[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------ norm-rescaled classifier-free guidance
+// RegionE/QwenImageEdit/inplace.py:386-405: comb = neg + s * (pos - neg); out = comb * (||pos|| / ||comb||), every
+// intermediate a bf16 tensor (row norms accumulate in fp32 and round to bf16). One warp per token.
+__global__ void __launch_bounds__(256) cfg_rescale_kernel(const __nv_bfloat16* __restrict__ pos,
+                                                          const __nv_bfloat16* __restrict__ neg, float scale,
+                                                          __nv_bfloat16* __restrict__ out, int M, int Cch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  float comb[4];
+  float sp = 0.f, sc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = lane + 32 * i;
+    comb[i] = 0.f;
+    if (ch < Cch) {
+      const long o = (long)m * Cch + ch;
+      const float p = __bfloat162float(pos[o]), n = __bfloat162float(neg[o]);
+      comb[i] = bf16_round(n + bf16_round(scale * bf16_round(p - n)));
+      sp += p * p;
+      sc += comb[i] * comb[i];
+    }
+  }
+  const float cond_norm = bf16_round(sqrtf(warp_sum(sp)));
+  const float noise_norm = bf16_round(sqrtf(warp_sum(sc)));
+  const float r = bf16_round(cond_norm / noise_norm);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < Cch) out[(long)m * Cch + ch] = __float2bfloat16_rn(comb[i] * r);
+  }
+}
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -373,6 +437,22 @@ cudaError_t launch_ln_modulate(const __nv_bfloat16* x, long ldx, const __nv_bflo
   if (D == 3072) ln_modulate_reg_kernel<12><<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
   else if (D == 256) ln_modulate_reg_kernel<1><<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
   else ln_modulate_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M, D);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long ldx, const __nv_bfloat16* w, __nv_bfloat16* out, long ldo,
+                           int M, int D, float eps, cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  if (D % 8 || ldx % 8 || ldo % 8) return cudaErrorInvalidValue;
+  rmsnorm_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ldx, w, out, ldo, M, D, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cfg_rescale(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale, __nv_bfloat16* out,
+                               int M, int Cch, cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  if (Cch > 128) return cudaErrorInvalidValue;
+  cfg_rescale_kernel<<<cdiv(M, 8), 256, 0, s>>>(pos, neg, scale, out, M, Cch);
   return cudaGetLastError();
 }
 

@@ -11,6 +11,13 @@ cudaError_t launch_ln_modulate(const __nv_bfloat16* x, long ldx, const __nv_bflo
                                const __nv_bfloat16* shift, __nv_bfloat16* out, long ldo, int M, int D,
                                cudaStream_t s);
 
+// out[m,:] = bf16(x[m,:] * rsqrt(mean(x^2) + eps)) * w     (diffusers RMSNorm with weight)
+cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long ldx, const __nv_bfloat16* w, __nv_bfloat16* out, long ldo,
+                           int M, int D, float eps, cudaStream_t s);
+// Norm-rescaled CFG: comb = neg + scale (pos - neg); out = comb * (|pos| / |comb|) per token.
+cudaError_t launch_cfg_rescale(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale, __nv_bfloat16* out,
+                               int M, int Cch, cudaStream_t s);
+
 // Batched GEMV: for every job j, out_j[n] = act_out(W_j[n,:] . act_in(x_j) + b_j[n]); one warp per output row.
 struct GemvJob {
   const __nv_bfloat16* W;  // [N, K]

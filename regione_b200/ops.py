@@ -72,6 +72,29 @@ def ln_modulate(x, scale, shift, out=None):
     return out
 
 
+def rmsnorm(x, weight, eps: float = 1e-6, out=None):
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x"); _req(weight, torch.bfloat16, "weight")
+    if out is None:
+        out = torch.empty_like(x)
+    M, Dm = x.shape
+    check(lib.rge_op_rmsnorm(ptr(x), x.stride(0), ptr(weight), ptr(out), out.stride(0), M, Dm, eps, stream_ptr()),
+          "rge_op_rmsnorm")
+    return out
+
+
+def cfg_rescale(pos, neg, scale: float, out=None):
+    """Norm-rescaled CFG on [M, channels] velocities."""
+    lib = _lib.load()
+    _req(pos, torch.bfloat16, "pos"); _req(neg, torch.bfloat16, "neg")
+    pos = pos.contiguous(); neg = neg.contiguous()
+    if out is None:
+        out = torch.empty_like(pos)
+    check(lib.rge_cfg_rescale(ptr(pos), ptr(neg), float(scale), ptr(out), pos.shape[0], pos.shape[1], stream_ptr()),
+          "rge_cfg_rescale")
+    return out
+
+
 def rope_table(ids: torch.Tensor) -> torch.Tensor:
     """ids fp32 [S,3] -> fp32 [S,64,2] (cos, sin)."""
     lib = _lib.load()
