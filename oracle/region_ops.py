@@ -105,7 +105,10 @@ class RegionState:
 
     def _split(self, latent, latent_ids):
         self.unedited_latent = gather_rows(latent, self.unedited_ids)
-        ids = gather_rows(latent_ids.unsqueeze(0), self.edited_ids).squeeze(0)
+        if latent_ids.dim() == 1:   # Qwen keeps 1-D position indices (QwenImageEdit/inplace.py:322)
+            ids = latent_ids[self.edited_ids.squeeze(0)]
+        else:
+            ids = gather_rows(latent_ids.unsqueeze(0), self.edited_ids).squeeze(0)
         return gather_rows(latent, self.edited_ids), ids
 
     def _merge(self, latent):

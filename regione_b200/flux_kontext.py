@@ -89,7 +89,7 @@ class RegionESchedulerMixin:
             raise ValueError("pass one of scheduler.timesteps, not an integer index")            # :594-605
         if self.step_index is None:
             self._init_step_index(timestep)                                                      # :606-607
-        M = MANAGER
+        M = getattr(self, "_regione_manager", MANAGER)   # each family module owns its singleton
         sig = self._host_sigmas()
         idx = self.step_index
         sigma, sigma_next = sig[idx], sig[idx + 1]
@@ -325,6 +325,7 @@ def warp_modules(pipeline, **args):
     pipeline.__class__ = type("RegionEFluxKontextPipeline", (RegionEFluxKontextPipelineMixin, saved["cls"]), {})
     sch_cls = type("RegionEFlowMatchEulerDiscreteScheduler", (RegionESchedulerMixin, saved["scheduler"].__class__), {})
     pipeline.scheduler = sch_cls.from_config(saved["scheduler"].config)
+    pipeline.scheduler._regione_manager = MANAGER
     tr.forward = types.MethodType(RegionEFluxTransformer2DModelforward, tr)
     for block in tr.transformer_blocks:
         block.attn.set_processor(RegionEB200AttnProcessor(False))

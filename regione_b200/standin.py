@@ -232,3 +232,95 @@ class FluxKontextPipeline:
 
 class Step1XEditPipeline(FluxKontextPipeline):
     pass
+
+
+# ------------------------------------------------------------------------------------------------ Qwen-Image-Edit
+class _ModSeq(nn.Sequential):
+    """diffusers `img_mod` / `txt_mod`: nn.Sequential(SiLU, Linear(dim, 6 dim)); index 1 is the Linear."""
+
+    def __init__(self, dim):
+        super().__init__(nn.SiLU(), nn.Linear(dim, 6 * dim))
+
+
+class _QwenBlock(nn.Module):
+    def __init__(self, dim, heads, ratio):
+        super().__init__()
+        self.img_mod, self.txt_mod = _ModSeq(dim), _ModSeq(dim)
+        self.attn = _Attention(dim, heads, context=True)
+        self.img_mlp, self.txt_mlp = _FeedForward(dim, ratio * dim), _FeedForward(dim, ratio * dim)
+
+
+class _QwenTimeEmbed(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.timestep_embedder = _MLPEmbed(256, dim)
+
+
+class QwenEmbedRope(nn.Module):
+    """Rotary table of Qwen-Image (diffusers QwenEmbedRope, theta 10000, axes (16, 56, 56), scale_rope=True),
+    restated: complex frequencies per (frame, row, column) with rows / columns centred around zero; text tokens
+    continue after the largest image extent. Returns (img_freqs [N, 64] complex64, txt_freqs [T, 64] complex64)."""
+
+    def __init__(self, theta=10000, axes_dim=(16, 56, 56)):
+        super().__init__()
+        self.theta, self.axes_dim = theta, axes_dim
+
+    def _table(self, index, dim):
+        freqs = torch.outer(index.float(), 1.0 / torch.pow(self.theta, torch.arange(0, dim, 2).float() / dim))
+        return torch.polar(torch.ones_like(freqs), freqs)
+
+    def forward(self, video_fhw, txt_seq_lens, device=None):
+        pos = torch.cat([self._table(torch.arange(4096), d) for d in self.axes_dim], dim=1)
+        neg = torch.cat([self._table(torch.arange(4096).flip(0) * -1 - 1, d) for d in self.axes_dim], dim=1)
+        if isinstance(video_fhw, list) and isinstance(video_fhw[0], list):
+            video_fhw = video_fhw[0]
+        out, max_vid = [], 0
+        a0, a1, a2 = [d // 2 for d in self.axes_dim]
+        for idx, (f, h, w) in enumerate(video_fhw):
+            fp = pos[:, :a0][idx:idx + f].view(f, 1, 1, -1).expand(f, h, w, -1)
+            hh = torch.cat([neg[:, a0:a0 + a1][-(h - h // 2):], pos[:, a0:a0 + a1][:h // 2]], dim=0)
+            ww = torch.cat([neg[:, a0 + a1:][-(w - w // 2):], pos[:, a0 + a1:][:w // 2]], dim=0)
+            hp = hh.view(1, h, 1, -1).expand(f, h, w, -1)
+            wp = ww.view(1, 1, w, -1).expand(f, h, w, -1)
+            out.append(torch.cat([fp, hp, wp], dim=-1).reshape(f * h * w, -1))
+            max_vid = max(max_vid, h // 2, w // 2)
+        txt = pos[max_vid:max_vid + max(txt_seq_lens)]
+        return torch.cat(out, dim=0).to(device), txt.to(device)
+
+
+class QwenImageTransformer2DModel(nn.Module):
+    """Weight container with the module surface of diffusers' QwenImageTransformer2DModel (60 dual-stream blocks)."""
+
+    def __init__(self, dim=3072, heads=24, n_blocks=60, mlp_ratio=4, in_channels=64, ctx_dim=3584):
+        super().__init__()
+        self.config = _Config(in_channels=in_channels, guidance_embeds=False, num_layers=n_blocks,
+                              attention_head_dim=dim // heads, num_attention_heads=heads, joint_attention_dim=ctx_dim)
+        self.img_in = nn.Linear(in_channels, dim)
+        self.txt_norm = _RMSNorm(ctx_dim)
+        self.txt_in = nn.Linear(ctx_dim, dim)
+        self.time_text_embed = _QwenTimeEmbed(dim)
+        self.pos_embed = QwenEmbedRope()
+        self.transformer_blocks = nn.ModuleList([_QwenBlock(dim, heads, mlp_ratio) for _ in range(n_blocks)])
+        self.norm_out = _AdaNorm(dim, 2)
+        self.proj_out = nn.Linear(dim, in_channels)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("the vanilla QwenImageTransformer2DModel.forward is diffusers code; enable RegionE")
+
+    init_synthetic = FluxTransformer2DModel.init_synthetic
+
+
+class QwenImageEditPipeline(FluxKontextPipeline):
+    """Stand-in with the class name `RegionEHelper` dispatches on (RegionE/tool/RegionE.py:5)."""
+
+    def __init__(self, transformer, scheduler=None):
+        super().__init__(transformer, scheduler)
+        self._attention_kwargs = None
+
+    @property
+    def _execution_device(self):
+        return self.transformer.img_in.weight.device
+
+    @property
+    def attention_kwargs(self):
+        return self._attention_kwargs

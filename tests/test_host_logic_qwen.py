@@ -1,0 +1,61 @@
+"""CPU tests of the Qwen-Image-Edit host side: dispatch on the pipeline class name, patching / restoring, the stand-in
+rotary table's contract, and the not-yet-built families failing loudly."""
+import pytest
+import torch
+
+from regione_b200 import RegionEHelper, params, standin
+from regione_b200 import qwen_image_edit as qw
+
+
+def _pipe(cls=standin.QwenImageEditPipeline):
+    tr = standin.QwenImageTransformer2DModel(dim=256, heads=2, n_blocks=2, mlp_ratio=4, in_channels=64, ctx_dim=64)
+    return cls(tr)
+
+
+def test_qwen_enable_disable():
+    """RegionE/QwenImageEdit/inplace.py:53-71."""
+    pipe = _pipe()
+    base_cls, base_sched = pipe.__class__, pipe.scheduler.__class__
+    h = RegionEHelper(pipe)
+    assert h.config["threshold"] == 0.80 and h.config["cache_threshold"] == 0.03       # RegionE.py:5
+    h.enable()
+    assert pipe.__class__.__name__ == "RegionEQwenImageEditPipeline" and isinstance(pipe, base_cls)
+    assert pipe.scheduler.__class__.__name__ == "RegionEFlowMatchEulerDiscreteScheduler"
+    assert pipe.scheduler._regione_manager is qw.MANAGER
+    assert all(b.attn.processor is not None for b in pipe.transformer.transformer_blocks)
+    assert qw.gamma == params.GAMMA["QwenImageEditPipeline"]
+    h.disable()
+    assert pipe.__class__ is base_cls and pipe.scheduler.__class__ is base_sched
+    assert "forward" not in pipe.transformer.__dict__
+
+
+def test_qwen_plus_uses_its_own_gamma():
+    class QwenImageEditPlusPipeline(standin.QwenImageEditPipeline):
+        pass
+    pipe = _pipe(QwenImageEditPlusPipeline)
+    h = RegionEHelper(pipe)
+    h.enable()
+    try:
+        assert qw.gamma == params.GAMMA["QwenImageEditPlusPipeline"] != params.GAMMA["QwenImageEditPipeline"]
+    finally:
+        h.disable()
+
+
+def test_qwen_rope_table_contract():
+    """pos_embed(img_shapes, txt_seq_lens) -> unit-modulus complex [L+C, 64] / [T, 64]; noise and condition images of
+    equal shape differ only in the frame axis (first 8 frequencies)."""
+    r = standin.QwenEmbedRope()
+    img, txt = r([[(1, 6, 10), (1, 6, 10)]], [7])
+    assert img.shape == (120, 64) and txt.shape == (7, 64) and img.dtype == torch.complex64
+    assert torch.allclose(img.abs(), torch.ones(120, 64), atol=1e-5)
+    assert torch.allclose(img[:60, 8:], img[60:, 8:]) and not torch.allclose(img[:60, :8], img[60:, :8])
+
+
+def test_step1x_not_built_fails_loudly():
+    class Step1XEditPipeline(standin.FluxKontextPipeline):
+        pass
+    tr = standin.FluxTransformer2DModel(dim=256, heads=2, n_double=1, n_single=1, ctx_dim=64, pooled_dim=32)
+    h = RegionEHelper(Step1XEditPipeline(tr))
+    assert h.config["threshold"] == 0.88
+    with pytest.raises(NotImplementedError):
+        h.enable()
