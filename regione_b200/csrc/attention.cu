@@ -14,6 +14,8 @@
 // Replaces flash_attn_func(q, k, v, causal=False) at RegionE/FluxKontext/inplace.py:796-801; K/V are read in place
 // from the Region-Instruction KV cache instead of being re-normalised, re-rotated and re-concatenated every step
 // (inplace.py:756-794).
+#include <cstdlib>
+
 #include "attention.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -56,10 +58,8 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
-#ifndef RGE_ATTN_POLY_EX2
-#define RGE_ATTN_POLY_EX2 1
-#endif
-
+// kPoly = how many of every four exponentials use ex2_poly instead of MUFU.EX2 (0, 1 or 2).
+template <int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnDev p) {
@@ -266,12 +266,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int jj = 64 * half; jj < 64 * half + 64; jj += 4) {
           const float p0 = ex2(fmaf(__uint_as_float(v[jj + 0]), sl2, neg_m));
           const float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
-          const float p2 = ex2(fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m));
-#if RGE_ATTN_POLY_EX2
-          const float p3 = ex2_poly(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
-#else
-          const float p3 = ex2(fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m));
-#endif
+          const float a2 = fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m);
+          const float a3 = fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m);
+          const float p2 = kPoly >= 2 ? ex2_poly(a2) : ex2(a2);
+          const float p3 = kPoly >= 1 ? ex2_poly(a3) : ex2(a3);
           sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
           v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
           v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
@@ -321,11 +319,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
   if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  static int poly = -1;
+  if (poly < 0) {
+    const char* env = getenv("RGE_ATTN_POLY");   // tuning knob: 0 (default, fastest measured), 1 or 2 of every 4 exponentials on the FMA pipe
+    poly = env ? atoi(env) : 0;
+    if (poly < 0 || poly > 2) poly = 0;
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   CUtensorMap mq, mk, mv;
   if (!make_tmap_bf16_2d(&mq, a.Q, a.Sq, (uint64_t)a.H * 128, a.ldq, kTile)) return cudaErrorInvalidValue;
@@ -338,7 +342,9 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.Skv = a.Skv;
   p.sl2 = a.scale * 1.4426950408889634f;
   dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
-  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  if (poly == 0) attention_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  else if (poly == 2) attention_kernel<2><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  else attention_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
 
