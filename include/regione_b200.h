@@ -82,6 +82,13 @@ int rge_op_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, in
 int rge_cfg_rescale(const void* pos, const void* neg, float scale, void* out, int32_t M, int32_t channels,
                     void* stream);
 
+/* Step1X classifier-free guidance (Step1XEdit/inplace.py:388-400): norm_out[m] = ||pos[m,:] - neg[m,:]|| (bf16 [M]);
+ * out = neg + scale * (pos - neg) / denom[m]   (denom bf16 [M] = the pipeline's process_diff_norm(diff_norm); NULL
+ * = plain CFG for t <= timesteps_truncate). */
+int rge_cfg_diff_norm(const void* pos, const void* neg, void* norm_out, int32_t M, int32_t channels, void* stream);
+int rge_cfg_combine(const void* pos, const void* neg, float scale, const void* denom, void* out, int32_t M,
+                    int32_t channels, void* stream);
+
 /* Rotary table of FluxPosEmbed(theta 10000, axes (16,56,56)): ids fp32 [S,3] -> cs fp32 [S,64,2] = (cos, sin). */
 int rge_op_rope_table(const float* ids, float* cs, int32_t S, void* stream);
 

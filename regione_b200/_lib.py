@@ -90,6 +90,8 @@ PROTOTYPES = {
                                      c_void_p]),
     "rge_op_rmsnorm": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "rge_cfg_rescale": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p]),
+    "rge_cfg_diff_norm": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "rge_cfg_combine": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "rge_op_rope_table": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p]),
     "rge_gather_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "rge_scatter_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),

@@ -193,6 +193,21 @@ int rge_cfg_rescale(const void* pos, const void* neg, float scale, void* out, in
   return RGE_OK;
 }
 
+int rge_cfg_diff_norm(const void* pos, const void* neg, void* norm_out, int32_t M, int32_t channels, void* stream) {
+  if (M > 0 && (!pos || !neg || !norm_out)) return fail(RGE_ERR_INVALID, "rge_cfg_diff_norm: null operand");
+  RGE_LAUNCH(launch_row_diff_norm((const bf16*)pos, (const bf16*)neg, (bf16*)norm_out, M, channels,
+                                  (cudaStream_t)stream));
+  return RGE_OK;
+}
+
+int rge_cfg_combine(const void* pos, const void* neg, float scale, const void* denom, void* out, int32_t M,
+                    int32_t channels, void* stream) {
+  if (M > 0 && (!pos || !neg || !out)) return fail(RGE_ERR_INVALID, "rge_cfg_combine: null operand");
+  RGE_LAUNCH(launch_cfg_combine((const bf16*)pos, (const bf16*)neg, scale, (const bf16*)denom, (bf16*)out, M, channels,
+                                (cudaStream_t)stream));
+  return RGE_OK;
+}
+
 int rge_op_rope_table(const float* ids, float* cs, int32_t S, void* stream) {
   if (!ids || !cs) return fail(RGE_ERR_INVALID, "rge_op_rope_table: null operand");
   RGE_LAUNCH(launch_rope_table(ids, (float2*)cs, S, (cudaStream_t)stream));

@@ -425,6 +425,35 @@ __global__ void __launch_bounds__(256) cfg_rescale_kernel(const __nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------ Step1X classifier-free guidance pieces
+// RegionE/Step1XEdit/inplace.py:388-400: diff_norm = ||pos - neg|| per token (bf16), then
+// out = neg + scale * (pos - neg) [/ denom], every intermediate a bf16 tensor. One warp per token.
+__global__ void __launch_bounds__(256) row_diff_norm_kernel(const __nv_bfloat16* __restrict__ pos,
+                                                            const __nv_bfloat16* __restrict__ neg,
+                                                            __nv_bfloat16* __restrict__ out, int M, int Cch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  float ss = 0.f;
+  for (int ch = lane; ch < Cch; ch += 32) {
+    const long o = (long)m * Cch + ch;
+    const float d = bf16_round(__bfloat162float(pos[o]) - __bfloat162float(neg[o]));
+    ss += d * d;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) out[m] = __float2bfloat16_rn(sqrtf(ss));
+}
+__global__ void cfg_combine_kernel(const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ neg,
+                                   float scale, const __nv_bfloat16* __restrict__ denom,
+                                   __nv_bfloat16* __restrict__ out, int M, int Cch) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * Cch) return;
+  const float p = __bfloat162float(pos[idx]), n = __bfloat162float(neg[idx]);
+  float e = bf16_round(scale * bf16_round(p - n));
+  if (denom) e = bf16_round(e / __bfloat162float(denom[idx / Cch]));
+  out[idx] = __float2bfloat16_rn(n + e);
+}
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -453,6 +482,20 @@ cudaError_t launch_cfg_rescale(const __nv_bfloat16* pos, const __nv_bfloat16* ne
   if (M <= 0) return cudaSuccess;
   if (Cch > 128) return cudaErrorInvalidValue;
   cfg_rescale_kernel<<<cdiv(M, 8), 256, 0, s>>>(pos, neg, scale, out, M, Cch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_diff_norm(const __nv_bfloat16* pos, const __nv_bfloat16* neg, __nv_bfloat16* out, int M,
+                                 int Cch, cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  row_diff_norm_kernel<<<cdiv(M, 8), 256, 0, s>>>(pos, neg, out, M, Cch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cfg_combine(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale,
+                               const __nv_bfloat16* denom, __nv_bfloat16* out, int M, int Cch, cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  cfg_combine_kernel<<<cdiv((long)M * Cch, 256), 256, 0, s>>>(pos, neg, scale, denom, out, M, Cch);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,12 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long ldx, const __nv_bfloat16
 cudaError_t launch_cfg_rescale(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale, __nv_bfloat16* out,
                                int M, int Cch, cudaStream_t s);
 
+// Step1X CFG: out[m] = bf16(|pos[m,:] - neg[m,:]|);  out = neg + scale (pos - neg) [/ denom[m]] in bf16 steps.
+cudaError_t launch_row_diff_norm(const __nv_bfloat16* pos, const __nv_bfloat16* neg, __nv_bfloat16* out, int M,
+                                 int Cch, cudaStream_t s);
+cudaError_t launch_cfg_combine(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale,
+                               const __nv_bfloat16* denom, __nv_bfloat16* out, int M, int Cch, cudaStream_t s);
+
 // Batched GEMV: for every job j, out_j[n] = act_out(W_j[n,:] . act_in(x_j) + b_j[n]); one warp per output row.
 struct GemvJob {
   const __nv_bfloat16* W;  // [N, K]

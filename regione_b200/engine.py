@@ -80,6 +80,11 @@ class FluxEngine:
         self._lin(g, 0, GS, "POOL2", tte.text_embedder.linear_2, "text_embedder.linear_2")
         self._lin(g, 0, GS, "NORM_OUT", tr.norm_out.linear, "norm_out.linear")
         self._lin(g, 0, GS, "PROJ_OUT", tr.proj_out, "proj_out")
+        self._register_blocks(blocks, singles)
+
+    def _register_blocks(self, blocks, singles):
+        """FLUX-style double / single blocks (shared with Step1X-Edit, whose block stack is the same)."""
+        d, s = _lib.BLK_DOUBLE, _lib.BLK_SINGLE
         for i, b in enumerate(blocks):
             n = f"transformer_blocks.{i}."
             a = b.attn

@@ -95,6 +95,32 @@ def cfg_rescale(pos, neg, scale: float, out=None):
     return out
 
 
+def cfg_diff_norm(pos, neg):
+    """bf16 [M]: per-token norm of (pos - neg)."""
+    lib = _lib.load()
+    _req(pos, torch.bfloat16, "pos"); _req(neg, torch.bfloat16, "neg")
+    pos = pos.contiguous(); neg = neg.contiguous()
+    out = torch.empty(pos.shape[0], dtype=torch.bfloat16, device=pos.device)
+    check(lib.rge_cfg_diff_norm(ptr(pos), ptr(neg), ptr(out), pos.shape[0], pos.shape[1], stream_ptr()),
+          "rge_cfg_diff_norm")
+    return out
+
+
+def cfg_combine(pos, neg, scale: float, denom=None, out=None):
+    """neg + scale * (pos - neg) [/ denom[m]] on [M, channels]."""
+    lib = _lib.load()
+    _req(pos, torch.bfloat16, "pos"); _req(neg, torch.bfloat16, "neg")
+    pos = pos.contiguous(); neg = neg.contiguous()
+    if denom is not None:
+        denom = denom.reshape(-1).contiguous()
+        _req(denom, torch.bfloat16, "denom")
+    if out is None:
+        out = torch.empty_like(pos)
+    check(lib.rge_cfg_combine(ptr(pos), ptr(neg), float(scale), ptr(denom), ptr(out), pos.shape[0], pos.shape[1],
+                              stream_ptr()), "rge_cfg_combine")
+    return out
+
+
 def rope_table(ids: torch.Tensor) -> torch.Tensor:
     """ids fp32 [S,3] -> fp32 [S,64,2] (cos, sin)."""
     lib = _lib.load()

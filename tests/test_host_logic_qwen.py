@@ -51,11 +51,22 @@ def test_qwen_rope_table_contract():
     assert torch.allclose(img[:60, 8:], img[60:, 8:]) and not torch.allclose(img[:60, :8], img[60:, :8])
 
 
-def test_step1x_not_built_fails_loudly():
-    class Step1XEditPipeline(standin.FluxKontextPipeline):
+def test_step1x_enable_disable_and_v1p2_not_built():
+    from regione_b200 import standin_step1x as sx
+    from regione_b200 import step1x_edit as s1
+    tr = sx.Step1XEditTransformer2DModel(dim=256, heads=2, n_double=1, n_single=1, ctx_dim=64, vec_dim=32)
+    pipe = sx.Step1XEditPipeline(tr)
+    h = RegionEHelper(pipe)
+    assert h.config["threshold"] == 0.88 and h.config["cache_threshold"] == 0.02     # RegionE.py:3
+    h.enable()
+    assert pipe.__class__.__name__ == "RegionEStep1XEditPipeline" and pipe.scheduler._regione_manager is s1.MANAGER
+    assert [b.attn.processor.single for b in list(tr.transformer_blocks) + list(tr.single_transformer_blocks)] == \
+        [False, True]
+    h.disable()
+    assert pipe.__class__ is sx.Step1XEditPipeline
+
+    class Step1XEditPipelineV1P2(sx.Step1XEditPipeline):
         pass
-    tr = standin.FluxTransformer2DModel(dim=256, heads=2, n_double=1, n_single=1, ctx_dim=64, pooled_dim=32)
-    h = RegionEHelper(Step1XEditPipeline(tr))
-    assert h.config["threshold"] == 0.88
+    h2 = RegionEHelper(Step1XEditPipelineV1P2(tr))
     with pytest.raises(NotImplementedError):
-        h.enable()
+        h2.enable()

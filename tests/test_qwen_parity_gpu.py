@@ -47,9 +47,10 @@ def _run(grid, txt_len, rho, params, cfg_scale, seed=7, n_blocks=3):
     helper.disable()
     assert tr_cu["modes"] == ref_tr["modes"]
     assert torch.equal(tr_cu["edited_ids"].cpu(), ref_tr["edited_ids"].squeeze(0).to(torch.int32))
+    v_tol = TOL * max(1.0, cfg_scale)   # guided velocity amplifies the two passes' bf16 rounding; the gate is on latents
     for i, (a, b) in enumerate(zip(tr_cu["noise_pred"], ref_tr["noise_pred"])):
         if ref_tr["modes"][i] != "SKIP":
-            assert rel_l2(a, b[0]) <= TOL, f"step {i} ({ref_tr['modes'][i]}): velocity rel-L2 {rel_l2(a, b[0]):.3e}"
+            assert rel_l2(a, b[0]) <= v_tol, f"step {i} ({ref_tr['modes'][i]}): velocity rel-L2 {rel_l2(a, b[0]):.3e}"
     for i, (a, b) in enumerate(zip(tr_cu["latents"], ref_tr["latents"])):
         assert rel_l2(a, b[0]) <= TOL, f"step {i}: latent rel-L2 {rel_l2(a, b[0]):.3e}"
     assert rel_l2(out, ref) <= TOL
