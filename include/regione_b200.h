@@ -204,6 +204,11 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
  *   ctx_embedded  [T, dim] text tokens after the family's own context embedding (may be NULL in begin and supplied per
  *                 step instead: Step1X's connector depends on the timestep, Step1XEdit/inplace.py:514-520)
  *   temb          [dim] conditioning vector the adaLN modulations are computed from */
+/* Text length of one pass (default rge_config.txt_len = the maximum). Step1X-Edit v1p2 runs the cond and uncond
+ * prompts with their own lengths (`txt_length` / `neg_txt_length`, Step1XEditV1P2/utils.py:444-445); the pass then
+ * uses rows [0, txt_len) for text and [txt_len, txt_len + L + C) for image tokens in its cache and rotary table.
+ * Call before rge_begin_image[_ex] of that pass. */
+int rge_set_pass_text_len(rge_handle* h, int32_t pass, int32_t txt_len);
 int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const void* ctx_embedded, void* stream);
 int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
                     const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out, void* stream);

@@ -113,3 +113,88 @@ def run_regione_step1x(model, params, latents, image_latents, latent_ids, text_i
             trace["noise_pred"].append(noise_pred.clone())
     trace["edited_ids"], trace["unedited_ids"] = st.edited_ids, st.unedited_ids
     return latents, trace
+
+
+class Step1XV1P2Oracle(Step1XOracle):
+    """Step1XEditV1P2/inplace.py:596-660 forward + :800-890 processor: per-tag caches and text lengths."""
+
+    def __init__(self, weights, heads, n_double, n_single, front):
+        super().__init__(weights, heads, n_double, n_single, front)
+        self._kc = {"cond": {}, "uncond": {}}
+        self._vc = {"cond": {}, "uncond": {}}
+
+    def forward_tag(self, st, hidden_states, e, timestep, img_ids, tag):
+        self.k_cache, self.v_cache = self._kc[tag], self._vc[tag]      # k/v_cache_even (cond) / _odd (uncond)
+        st.txt_length = e.txt_ids.shape[0]                             # txt_length / neg_txt_length (:833, :868)
+        f = self.front
+        enc, y = f.connector(e.embedding, timestep, e.mask)
+        if getattr(f, "text_token_mapping", None) is not None:         # :606-609
+            enc = enc + f.text_token_mapping(e.text_embeds) * e.text_masks[:, :, None].to(enc.dtype)
+        h = self.lin("x_embedder", hidden_states)
+        temb = f.time_embed(f.time_proj(timestep * 1000).to(timestep)) + f.vec_embed(y)
+        enc = self.lin("context_embedder", enc)
+        rope_q = rope_cos_sin(torch.cat((e.txt_ids, img_ids), dim=0))
+        rope_k = rope_cos_sin(torch.cat((e.txt_ids, st.latent_ids), dim=0))
+        for i in range(self.n_double):
+            enc, h = self.double_block(i, h, enc, temb, rope_q, rope_k, st)
+        for i in range(self.n_single):
+            enc, h = self.single_block(i, h, enc, temb, rope_q, rope_k, st)
+        scale, shift = self.lin("norm_out.linear", F.silu(temb).to(h.dtype)).chunk(2, dim=1)
+        h = self._ln(h) * (1 + scale)[:, None, :] + shift[:, None, :]
+        return self.lin("proj_out", h)
+
+
+def run_regione_step1x_v1p2(model, params, gamma, latents, image_latents, latent_ids, pe, ne, true_cfg_scale,
+                            process_diff_norm, height, width, timesteps_truncate=0.93, process_norm_power=0.4,
+                            record=False):
+    """Step1XEditV1P2/inplace.py:347-458 (denoising part) for output_type='latent'."""
+    st = ro.RegionState()
+    st.set_parameters(params)
+    sigmas, timesteps = flow_match_sigmas(params["num_inference_steps"], latents.shape[1])
+    sch = EulerState(sigmas, timesteps)
+    g = torch.tensor(gamma, dtype=torch.float16)
+    st.refresh(latents, image_latents, latent_ids, pe.txt_ids, height, width)
+    cache, accumulate = None, 1
+    trace = {"modes": [], "latents": [], "noise_pred": []}
+    for i, t in enumerate(timesteps):
+        assert i == st.current_step
+        cur, N = st.current_step, st.inference_step
+        if cur <= st.warmup_step or cur > N - st.post_step - 1 or cur == st.prev_refresh_step:
+            should_cache, accumulate = False, 1
+        else:
+            ratio = g[i - 1] * (1 + (t - timesteps[i - 1]) / 1000)
+            if ratio >= 1:
+                should_cache, accumulate = False, 1
+            else:
+                accumulate = accumulate * ratio
+                if 1 - accumulate > st.cache_threshold:
+                    should_cache, accumulate = False, 1
+                else:
+                    should_cache = True
+        if should_cache:
+            if cache.shape[1] != latents.shape[1]:
+                cache = ro.gather_rows(cache, st.edited_ids)
+            noise_pred = scalar_times(ratio, cache)
+            trace["modes"].append("SKIP")
+        else:
+            x_in = latents
+            full = cur <= st.warmup_step - 1 or cur > N - st.post_step - 1 or cur == st.prev_refresh_step
+            if full:
+                x_in = torch.cat([latents, image_latents], dim=1)
+            timestep = t.expand(latents.shape[0]).to(latents.dtype)
+            pos = model.forward_tag(st, x_in, pe, timestep / 1000, latent_ids, "cond")[:, : latents.size(1)]
+            neg = model.forward_tag(st, x_in, ne, timestep / 1000, latent_ids, "uncond")[:, : latents.size(1)]
+            if t.item() > timesteps_truncate:
+                diff_norm = torch.norm(pos - neg, dim=(2), keepdim=True)
+                noise_pred = neg + true_cfg_scale * (pos - neg) / process_diff_norm(diff_norm, k=process_norm_power)
+            else:
+                noise_pred = neg + true_cfg_scale * (pos - neg)
+            cache = noise_pred
+            trace["modes"].append("FULL" if full else "REGION")
+        latents = scheduler_step(sch, st, noise_pred, latents, trace)
+        latents, latent_ids = st.step(latents, latent_ids)
+        if record:
+            trace["latents"].append(latents.clone())
+            trace["noise_pred"].append(noise_pred.clone())
+    trace["edited_ids"], trace["unedited_ids"] = st.edited_ids, st.unedited_ids
+    return latents, trace

@@ -106,6 +106,7 @@ PROTOTYPES = {
     "rge_set_weight": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "rge_finalize_weights": (c_int32, [c_void_p]),
     "rge_begin_image": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "rge_set_pass_text_len": (c_int32, [c_void_p, c_int32, c_int32]),
     "rge_begin_image_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "rge_dit_step_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int32, c_void_p]),

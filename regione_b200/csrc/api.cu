@@ -260,6 +260,7 @@ struct rge_handle {
   std::vector<const void*> gw, dw, sw;
   bool finalized = false;
   std::vector<char> begun;
+  std::vector<int> Tp;   // text length of each pass (<= T); Step1X-Edit v1p2 runs cond / uncond prompts of different length
   // workspaces
   bf16 *h = nullptr, *n = nullptr, *q = nullptr, *big = nullptr;
   bf16 *kcache = nullptr, *vcache = nullptr;
@@ -340,6 +341,7 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   h->dw.assign((size_t)cfg->n_double * RGE_D_NUM_SLOTS, nullptr);
   h->sw.assign((size_t)cfg->n_single * RGE_S_NUM_SLOTS, nullptr);
   h->begun.assign(cfg->n_pass, 0);
+  h->Tp.assign(cfg->n_pass, cfg->txt_len);
   const size_t S = h->S, D = h->D;
   h->n_mod = cfg->n_double * 2 + cfg->n_single + 1;
   const size_t mods_elems = (size_t)cfg->n_double * 12 * D + (size_t)cfg->n_single * 3 * D + 2 * D;
@@ -492,16 +494,16 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
   if (h->cfg.external_embed) return fail(RGE_ERR_STATE, "rge_begin_image: handle uses rge_begin_image_ex");
   if (h->cfg.pooled_dim == 0) return fail(RGE_ERR_UNSUPPORTED, "rge_begin_image: pooled_dim 0 needs external_embed");
   cudaStream_t st = (cudaStream_t)stream;
-  const int D = h->D, T = h->T;
+  const int D = h->D, T = h->Tp[pass];
   // key-side rotary table over the FULL sequence (MANAGER.image_rotary_emb, inplace.py:499); query rows are
   // looked up in the same table through the selection, which equals pos_embed(gathered ids) (:495-496)
   if (T > 0) RGE_CUDA(cudaMemcpyAsync(h->ids, txt_ids, (size_t)T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RGE_CUDA(cudaMemcpyAsync(h->ids + (size_t)T * 3, img_ids, (size_t)(h->L + h->C) * 3 * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
-  RGE_LAUNCH(launch_rope_table(h->ids, h->rope + (size_t)pass * h->S * 64, h->S, st));
+  RGE_LAUNCH(launch_rope_table(h->ids, h->rope + (size_t)pass * h->S * 64, T + h->L + h->C, st));
   // context_embedder (inplace.py:480): same value every step of the image, so computed once
   RGE_TRY(gemm(h, st, (const bf16*)enc, h->cfg.ctx_dim, T, h->cfg.ctx_dim, h->G(RGE_G_CTX_EMBED_W),
-               h->G(RGE_G_CTX_EMBED_B), D, EPI_STORE, h->ctx + (size_t)pass * T * D, D, nullptr, 0, 0));
+               h->G(RGE_G_CTX_EMBED_B), D, EPI_STORE, h->ctx + (size_t)pass * h->T * D, D, nullptr, 0, 0));
   // guidance / pooled halves of time_text_embed (inplace.py:475-479)
   bf16* gproj = h->ps(pass);
   bf16* pooled_buf = gproj + 256 + 2 * D;
@@ -525,9 +527,9 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
                 h->L + h->C);
   if (n_out < 0 || n_out > n_img) return fail(RGE_ERR_INVALID, "rge_dit_step: n_out %d > n_img %d", n_out, n_img);
   cudaStream_t st = (cudaStream_t)stream;
-  const int D = h->D, T = h->T, Dm = h->Dm, S = h->S, M = n_img, MA = T + n_img;
+  const int D = h->D, T = h->Tp[pass], Dm = h->Dm, S = T + h->L + h->C, M = n_img, MA = T + n_img;
   const long ldb = D + Dm;  // `big`: attention output in columns [0,D), MLP hidden in [D, D+Dm)
-  const float2* rope = h->rope + (size_t)pass * S * 64;
+  const float2* rope = h->rope + (size_t)pass * h->S * 64;
   bf16* tproj = h->small;
   bf16* t2 = tproj + 256 + D;
   bf16* temb = t2 + D;
@@ -552,7 +554,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   RGE_LAUNCH(launch_gemv_batch(h->jobs + 2, h->n_mod, 6 * D, st));
   // ---- token embedding: text rows [0,T) come from the per-image context embedding, image rows from x_embedder
   if (T > 0)
-    RGE_CUDA(cudaMemcpyAsync(h->h, ext_ctx ? (const bf16*)ext_ctx : h->ctx + (size_t)pass * T * D,
+    RGE_CUDA(cudaMemcpyAsync(h->h, ext_ctx ? (const bf16*)ext_ctx : h->ctx + (size_t)pass * h->T * D,
                              (size_t)T * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
   RGE_TRY(gemm(h, st, (const bf16*)x_in, h->cfg.in_channels, M, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
                h->G(RGE_G_X_EMBED_B), D, EPI_STORE, h->h, D, nullptr, T, 0));
@@ -674,6 +676,16 @@ int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img
   return dit_step_impl(h, pass, x_in, n_img, sel, 0.f, temb, ctx_embedded, v_out, n_out, stream);
 }
 
+int rge_set_pass_text_len(rge_handle* h, int32_t pass, int32_t txt_len) {
+  if (!h) return fail(RGE_ERR_INVALID, "rge_set_pass_text_len: null handle");
+  if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_set_pass_text_len: bad pass %d", pass);
+  if (txt_len < 0 || txt_len > h->T)
+    return fail(RGE_ERR_INVALID, "rge_set_pass_text_len: %d outside [0, %d]", txt_len, h->T);
+  h->Tp[pass] = txt_len;
+  h->begun[pass] = 0;   // the rotary table / context of the pass must be re-supplied for the new length
+  return RGE_OK;
+}
+
 int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const void* ctx_embedded, void* stream) {
   if (!h || !rope_cs) return fail(RGE_ERR_INVALID, "rge_begin_image_ex: null argument");
   if (!h->finalized) return fail(RGE_ERR_STATE, "rge_begin_image_ex: weights not finalized");
@@ -682,11 +694,12 @@ int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const 
   if (!(h->cfg.external_embed & 2) && (h->cfg.guidance_embeds || h->cfg.pooled_dim > 0))
     return fail(RGE_ERR_UNSUPPORTED, "rge_begin_image_ex: guidance / pooled embeddings need an external temb");
   cudaStream_t st = (cudaStream_t)stream;
-  RGE_CUDA(cudaMemcpyAsync(h->rope + (size_t)pass * h->S * 64, rope_cs, (size_t)h->S * 64 * sizeof(float2),
-                           cudaMemcpyDeviceToDevice, st));
-  if (ctx_embedded && h->T > 0)
+  const int Tp = h->Tp[pass];
+  RGE_CUDA(cudaMemcpyAsync(h->rope + (size_t)pass * h->S * 64, rope_cs,
+                           (size_t)(Tp + h->L + h->C) * 64 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  if (ctx_embedded && Tp > 0)
     RGE_CUDA(cudaMemcpyAsync(h->ctx + (size_t)pass * h->T * h->D, ctx_embedded,
-                             (size_t)h->T * h->D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+                             (size_t)Tp * h->D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
   h->begun[pass] = 1;
   return RGE_OK;
 }

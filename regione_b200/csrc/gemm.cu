@@ -9,6 +9,7 @@
 // (RegionE/FluxKontext/fused_kernels.py:9-101): the scatter is the `row_map` of the epilogue, and the
 // per-head RMSNorm + RoPE the reference re-applies to the whole cache every step
 // (RegionE/FluxKontext/inplace.py:756-763, 792-794) is fused here so the cache holds post-norm/post-RoPE rows.
+// Large-M launches are routed to the CTA-pair kernel in gemm2.cu; the epilogues live in gemm_epilogue.cuh.
 #include <cstdlib>
 
 #include "gemm.cuh"
@@ -34,8 +35,6 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
   static constexpr int kTmemCols = 2 * BN;
 };
-
-__device__ __forceinline__ float ldg_bf16(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -137,106 +136,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       const int acc = it & 1;
       const uint32_t use = (it >> 1) & 1;
-      const int m = m_blk * BM + r;
-      const bool valid = m < p.M;
-      const long out_row = valid ? (long)((p.row_map ? __ldg(p.row_map + m) : m) + p.row_off) : 0;
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      const int n_base = n_blk * BN;
-      __nv_bfloat16* out_ptr = p.out + out_row * p.ldo + p.col_off;
-
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
-
-      if constexpr (EPI == EPI_NORM_ROPE) {
-        const long rope_row = valid ? (long)((p.rope_map ? __ldg(p.rope_map + m) : m) + p.rope_off) : 0;
-        const float2* cs_row = p.rope_cs + rope_row * 64;
-#pragma unroll 1
-        for (int h = 0; h < BN / 128; ++h) {
-          const int n0 = n_base + h * 128;
-          if (n0 >= p.N) break;
-          float ss = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr + h * 128 + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float b = p.bias ? ldg_bf16(p.bias + n0 + c * 32 + j) : 0.f;
-              float x = bf16_round(__uint_as_float(v[j]) + b);
-              ss += x * x;
-            }
-          }
-          const float rstd = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(taddr + h * 128 + c * 32, v);
-            tmem_ld_wait();
-            uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int d = c * 32 + j;
-              float b0 = p.bias ? ldg_bf16(p.bias + n0 + d) : 0.f;
-              float b1 = p.bias ? ldg_bf16(p.bias + n0 + d + 1) : 0.f;
-              float x0 = bf16_round(__uint_as_float(v[j]) + b0);
-              float x1 = bf16_round(__uint_as_float(v[j + 1]) + b1);
-              x0 = bf16_round(bf16_round(x0 * rstd) * ldg_bf16(p.norm_w + d));
-              x1 = bf16_round(bf16_round(x1 * rstd) * ldg_bf16(p.norm_w + d + 1));
-              float2 cs = valid ? __ldg(cs_row + (d >> 1)) : make_float2(1.f, 0.f);
-              o[j >> 1] = pack_bf16x2(x0 * cs.x - x1 * cs.y, x1 * cs.x + x0 * cs.y);
-            }
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0 + c * 32);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n0 = n_base + c * 32;
-          if (n0 >= p.N) break;
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          uint32_t o[16];
-          uint4 rv[4];
-          if constexpr (EPI == EPI_GATE_RES) {
-            if (valid) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long)m * p.ldr + n0);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) rv[t] = rp[t];
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) rv[t] = make_uint4(0, 0, 0, 0);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float b0 = p.bias ? ldg_bf16(p.bias + n0 + j) : 0.f;
-            float b1 = p.bias ? ldg_bf16(p.bias + n0 + j + 1) : 0.f;
-            float x0 = bf16_round(__uint_as_float(v[j]) + b0);
-            float x1 = bf16_round(__uint_as_float(v[j + 1]) + b1);
-            if constexpr (EPI == EPI_GELU) {
-              x0 = gelu_tanh(x0);
-              x1 = gelu_tanh(x1);
-            } else if constexpr (EPI == EPI_GATE_RES) {
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-              __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(&rw[j >> 1]);
-              x0 = __bfloat162float(rr.x) + bf16_round(ldg_bf16(p.gate + n0 + j) * x0);
-              x1 = __bfloat162float(rr.y) + bf16_round(ldg_bf16(p.gate + n0 + j + 1) * x1);
-            }
-            o[j >> 1] = pack_bf16x2(x0, x1);
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-          }
-        }
-      }
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+      gemm_epilogue_row<BN, EPI>(p, taddr, m_blk * BM + r, n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -261,11 +164,7 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   CUtensorMap map_a, map_b;
   if (!make_tmap_bf16_2d(&map_a, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
-  GemmDev p;
-  p.M = a.M; p.N = a.N; p.K = a.K;
-  p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.row_map = a.row_map; p.row_off = a.row_off; p.col_off = a.col_off;
-  p.gate = a.gate; p.res = a.res; p.ldr = a.ldr;
-  p.norm_w = a.norm_w; p.rope_cs = a.rope_cs; p.rope_map = a.rope_map; p.rope_off = a.rope_off;
+  const GemmDev p = to_dev(a);
   const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   gemm_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(map_a, map_b, p);

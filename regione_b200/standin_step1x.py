@@ -91,3 +91,15 @@ class Step1XEditPipeline(FluxKontextPipeline):
     def process_diff_norm(diff_norm, k):
         """Fork's norm compression for CFG (Step1XEdit/inplace.py:407): norms above 1 are raised to the power k."""
         return torch.where(diff_norm > 1.0, torch.pow(diff_norm, k), torch.ones_like(diff_norm))
+
+
+class Step1XEditV1P2Transformer2DModel(Step1XEditTransformer2DModel):
+    """v1p2 adds `text_token_mapping` on an extra text-embedding stream (Step1XEditV1P2/inplace.py:606-609)."""
+
+    def __init__(self, text_dim=96, ctx_dim=4096, **kw):
+        super().__init__(ctx_dim=ctx_dim, **kw)
+        self.text_token_mapping = nn.Linear(text_dim, ctx_dim)
+
+
+class Step1XEditPipelineV1P2(Step1XEditPipeline):
+    pass

@@ -51,7 +51,7 @@ def test_qwen_rope_table_contract():
     assert torch.allclose(img[:60, 8:], img[60:, 8:]) and not torch.allclose(img[:60, :8], img[60:, :8])
 
 
-def test_step1x_enable_disable_and_v1p2_not_built():
+def test_step1x_enable_disable_both_versions():
     from regione_b200 import standin_step1x as sx
     from regione_b200 import step1x_edit as s1
     tr = sx.Step1XEditTransformer2DModel(dim=256, heads=2, n_double=1, n_single=1, ctx_dim=64, vec_dim=32)
@@ -67,6 +67,11 @@ def test_step1x_enable_disable_and_v1p2_not_built():
 
     class Step1XEditPipelineV1P2(sx.Step1XEditPipeline):
         pass
-    h2 = RegionEHelper(Step1XEditPipelineV1P2(tr))
-    with pytest.raises(NotImplementedError):
-        h2.enable()
+    from regione_b200 import step1x_edit_v1p2 as s2
+    pipe2 = Step1XEditPipelineV1P2(tr)
+    h2 = RegionEHelper(pipe2)
+    h2.enable()
+    assert pipe2.__class__.__name__ == "RegionEStep1XEditPipelineV1P2"
+    assert pipe2.scheduler._regione_manager is s2.MANAGER and s2.gamma == params.GAMMA["Step1XEditPipelineV1P2"]
+    h2.disable()
+    assert pipe2.__class__ is Step1XEditPipelineV1P2
