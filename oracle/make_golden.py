@@ -170,9 +170,56 @@ def make_schedule(u):
     return out
 
 
+FAMILY_DIRS = {"FluxKontextPipeline": "FluxKontext", "Step1XEditPipeline": "Step1XEdit",
+               "Step1XEditPipelineV1P2": "Step1XEditV1P2", "QwenImageEditPipeline": "QwenImageEdit",
+               "QwenImageEditPlusPipeline": "QwenImageEditPlus"}
+CLI_DIRS = ["FluxKontext", "Step1X-Edit", "Step1X-Edit-v1p2", "Qwen-Image", "Qwen-Image-Edit-2509"]
+
+
+def make_front_end(u):
+    """Constants and small host functions either side of the loop, produced by the reference's own code:
+    calculate_shift (utils.py:38-48) on a sweep of token counts, every family's gamma table (inplace.py:47-50) and
+    plugin defaults (tool/RegionE.py:1-7), and the argparse surface of src/<Family>/main.py:13-32 (the lines between
+    `ArgumentParser()` and `parse_args()` exec'd against a real argparse)."""
+    import argparse
+    import json
+    out = {"calculate_shift": {}, "gamma": {}, "defaults": {}, "cli": {}}
+    for n in [256, 1024, 2304, 3600, 4050, 4096, 4104, 6400, 8192]:
+        out["calculate_shift"][str(n)] = float(u.calculate_shift(n)).hex()
+    out["calculate_shift_custom"] = float(u.calculate_shift(4050, 256, 8192, 0.5, 0.9)).hex()
+    for name, d in FAMILY_DIRS.items():
+        src = open(f"{REF}/{d}/inplace.py").read().split("\n")
+        first = next(i for i, line in enumerate(src) if line.startswith("gamma = torch.tensor("))
+        last = next(i for i in range(first, first + 8) if "dtype=torch.float16)" in src[i])
+        ns = {"torch": torch}
+        exec("\n".join(src[first:last + 1]), ns)
+        out["gamma"][name] = [float(x) for x in ns["gamma"].tolist()]          # fp16 values, exactly representable
+    ns = {}
+    exec(ref_lines(f"{REF}/tool/RegionE.py", 1, 7), ns)
+    out["defaults"] = ns["config"]
+    for d in CLI_DIRS:
+        src = open(f"{REF}/../src/{d}/main.py").read().split("\n")
+        first = next(i for i, line in enumerate(src) if "argparse.ArgumentParser()" in line)
+        last = next(i for i, line in enumerate(src) if "parser.parse_args()" in line)
+        ns = {"argparse": argparse}
+        exec(textwrap.dedent("\n".join(src[first:last])), ns)
+        flags = {}
+        for a in ns["parser"]._actions:
+            if a.dest == "help":
+                continue
+            flags[a.dest] = dict(default=a.default, type=getattr(a.type, "__name__", None),
+                                 flag=isinstance(a, argparse._StoreTrueAction))
+        out["cli"][d] = flags
+    with open(os.path.join(OUT, "front_end.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     u = load_reference_utils("FluxKontext")
+    fe = make_front_end(u)
+    print("front end:", {k: len(v) if hasattr(v, "__len__") else v for k, v in fe.items()})
     cases = make_region_ops(u)
     for c in cases:
         print(f"selector seed {c['seed']} grid {c['gh']}x{c['gw']}: edited {c['edited'].shape[1]} "

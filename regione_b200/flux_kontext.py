@@ -20,15 +20,10 @@ from . import ops
 from .engine import FluxEngine
 from .manager import RegionManager, plan_steps
 from .params import GAMMA, SCALAR_ROUNDS_TO_BF16
+from .schedule import calculate_shift, retrieve_timesteps
 
 gamma = GAMMA["FluxKontextPipeline"]          # inplace.py:47-50
 MANAGER = RegionManager()                     # inplace.py:51 (module-global singleton, one pipeline per process)
-
-
-def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.15):
-    """Linear interpolation of the schedule shift mu in the token count (utils.py:38-48)."""
-    slope = (max_shift - base_shift) / (max_seq_len - base_seq_len)
-    return base_shift + slope * (image_seq_len - base_seq_len)
 
 
 _MASK_ALLGATHER = False
@@ -80,8 +75,10 @@ class RegionESchedulerMixin:
             self._regione_host_sigmas = hs
         return hs
 
-    def set_timesteps(self, *a, **k):
-        super().set_timesteps(*a, **k)
+    def set_timesteps(self, num_inference_steps=None, device=None, sigmas=None, mu=None, timesteps=None):
+        # explicit signature: retrieve_timesteps inspects it for `sigmas` / `timesteps` (utils.py:84-99)
+        kw = {} if timesteps is None else {"timesteps": timesteps}
+        super().set_timesteps(num_inference_steps, device=device, sigmas=sigmas, mu=mu, **kw)
         self._regione_host_sigmas = None
 
     def step(self, model_output, timestep, sample, *args, return_dict=True, reuse_ratio=None, **kwargs):
@@ -232,7 +229,7 @@ class RegionEFluxKontextPipelineMixin:
         cfg = self.scheduler.config
         mu = calculate_shift(latents.shape[1], cfg.get("base_image_seq_len", 256), cfg.get("max_image_seq_len", 4096),
                              cfg.get("base_shift", 0.5), cfg.get("max_shift", 1.15))
-        self.scheduler.set_timesteps(sigmas=sigmas, device=device, mu=mu)
+        retrieve_timesteps(self.scheduler, num_inference_steps, device, sigmas=sigmas, mu=mu)     # :238-244
         self.scheduler.set_begin_index(0)   # known start: spares _init_step_index's device lookup (:606-607)
         self.scheduler._step_index = 0
         latents = self.regione_denoise(latents, image_latents, latent_ids, text_ids, prompt_embeds,

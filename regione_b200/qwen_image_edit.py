@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 from .engine_qwen import QwenEngine
-from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift
+from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
 
@@ -97,7 +97,7 @@ class RegionEQwenImageEditPipelineMixin:
         cfg = self.scheduler.config
         mu = calculate_shift(latents.shape[1], cfg.get("base_image_seq_len", 256), cfg.get("max_image_seq_len", 4096),
                              cfg.get("base_shift", 0.5), cfg.get("max_shift", 1.15))
-        self.scheduler.set_timesteps(sigmas=sigmas, device=device, mu=mu)
+        retrieve_timesteps(self.scheduler, num_inference_steps, device, sigmas=sigmas, mu=mu)
         self.scheduler.set_begin_index(0)                                                            # :326
         self.scheduler._step_index = 0
         txt_lens = [prompt_embeds.shape[1]] if prompt_embeds_mask is None else prompt_embeds_mask.sum(dim=1).tolist()

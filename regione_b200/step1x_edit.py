@@ -22,7 +22,7 @@ from . import _lib, ops
 from ._lib import G as GS
 from ._lib import check, ptr, stream_ptr
 from .engine import FluxEngine
-from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift
+from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
 
@@ -142,7 +142,7 @@ class RegionEStep1XEditPipelineMixin:
         cfg = self.scheduler.config
         mu = calculate_shift(latents.shape[1], cfg.get("base_image_seq_len", 256), cfg.get("max_image_seq_len", 4096),
                              cfg.get("base_shift", 0.5), cfg.get("max_shift", 1.15))
-        self.scheduler.set_timesteps(sigmas=sigmas, device=device, mu=mu)
+        retrieve_timesteps(self.scheduler, num_inference_steps, device, sigmas=sigmas, mu=mu)
         self.scheduler.set_begin_index(0)                                                         # :336
         self.scheduler._step_index = 0
         do_true_cfg = true_cfg_scale > 1 and negative_prompt_embeds is not None

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift
+from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
 from .step1x_edit import Step1XEngine
@@ -94,7 +94,7 @@ class RegionEStep1XEditV1P2PipelineMixin:
         cfg = self.scheduler.config
         mu = calculate_shift(latents.shape[1], cfg.get("base_image_seq_len", 256), cfg.get("max_image_seq_len", 4096),
                              cfg.get("base_shift", 0.5), cfg.get("max_shift", 1.15))
-        self.scheduler.set_timesteps(sigmas=sigmas, device=device, mu=mu)
+        retrieve_timesteps(self.scheduler, num_inference_steps, device, sigmas=sigmas, mu=mu)
         self.scheduler.set_begin_index(0)
         self.scheduler._step_index = 0
         out = self.regione_denoise(latents, image_latents, latent_ids, prompt_embeds, negative_prompt_embeds,
