@@ -210,7 +210,11 @@ def run_ours(args):
     sampler.start()
     lib.rge_profile_enable(1)
     launches0 = lib.rge_launch_count()
+    if args.profiler_range:           # ncu --profile-from-start off: capture exactly the timed images
+        torch.cuda.profiler.start()
     ms = timed(image_resident, args.steps)
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     launches = lib.rge_launch_count() - launches0
     pms, psum, pwork, pcnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int64 * 2)()
     lib.rge_profile_collect(pms, psum, pwork, pcnt)
@@ -296,19 +300,83 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_reference_gpu(args):
+    """EXTRA arm (not the driver's `--impl reference`): the reference-equivalent PyTorch path of SURVEY §8d on the
+    SAME GPU — the oracle restatement run in eager torch on cuda:0 with flash-attn's `flash_attn_func` where the
+    reference calls it (inplace.py:796-801) and a bf16 tensor-core GEMM + fp16 round trip where it calls its Triton
+    `_partially_linear` (fused_kernels.py:81-101; the Triton source lives in /root/reference, which does not exist on
+    the GPU box). 3 warm-up images and
+    `cuda.synchronize()` + wall clock around each image, as src/FluxKontext/main.py:49-73 does."""
+    import torch.nn.functional as F
+    import oracle.flux as of
+    from flash_attn import flash_attn_func
+    from oracle.loop import run_regione
+    from oracle.schedule import GAMMA
+    from regione_b200 import synthetic as syn
+    from regione_b200.standin import latent_image_ids
+
+    dev = torch.device("cuda", 0)
+
+    def fa(q, k, v):                       # [B,H,S,hd] like the processor after RoPE; flash-attn wants [B,S,H,hd]
+        o = flash_attn_func(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=False)
+        return o.reshape(o.shape[0], o.shape[1], -1)
+
+    def pl(x, w, b, index, cache):
+        cache[:, index, :] = F.linear(x, w, b).to(torch.float16).to(cache.dtype)
+
+    of.exact_attention, of.partially_linear = fa, pl
+    arch = syn.FLUX_KONTEXT
+    pipe = syn.build_pipeline(arch, seed=110, device=dev)
+    w = {k: v.detach() for k, v in pipe.transformer.state_dict().items()}
+    model = of.FluxOracle(w, arch["heads"], arch["n_double"], arch["n_single"], True)
+    inp = syn.make_inputs(110, GRID, GRID, TXT, arch["ctx_dim"], arch["pooled_dim"], rho=args.rho, device=dev)
+    ids = torch.cat([latent_image_ids(GRID, GRID, 0.0, dev), latent_image_ids(GRID, GRID, 1.0, dev)])
+    txt_ids = torch.zeros(TXT, 3, device=dev)
+
+    def image():
+        with torch.no_grad():
+            return run_regione(model, dict(num_inference_steps=28, **PARAMS), GAMMA["FluxKontext"], inp["latents"],
+                               inp["image_latents"], ids, txt_ids, inp["prompt_embeds"], inp["pooled_prompt_embeds"],
+                               2.5, inp["height"], inp["width"])
+
+    for _ in range(args.warmup):
+        out, tr = image()
+    times = []
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out, tr = image()
+        torch.cuda.synchronize()
+        times.append(time.time() - t0)
+    sec = sum(times) / len(times)
+    print(json.dumps({
+        "impl": "reference_gpu", "metric": METRIC, "value": round(1.0 / sec, 4), "unit": "images/sec", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]; reference-equivalent eager PyTorch path on the same B200: oracle "
+                               "restatement + flash_attn_func (flash-attn 2.8) + cuBLAS bf16; same weights, inputs, "
+                               "schedule as our arm", "schedule": "".join(m[0] for m in tr["modes"]),
+                   "edited_tokens": int(tr["edited_ids"].numel()), "rho_target": args.rho},
+        "per_image_s": [round(t, 4) for t in times]}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--rho", type=float, default=0.25, help="target edited fraction of the synthetic image")
     ap.add_argument("--arch", default="flux", choices=["flux", "tiny"])
     ap.add_argument("--ref-edited", type=int, default=1200, help="edited tokens of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed (device-resident) images, for ncu launch lists")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference_gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RGE_ABI_VERSION 2
+#define RGE_ABI_VERSION 3
 
 enum rge_status {
   RGE_OK = 0,
@@ -97,6 +97,15 @@ int rge_gather_rows(const void* src, int64_t lds, const int32_t* ids, int32_t n,
                     int64_t ldd, void* stream);
 int rge_scatter_rows(const void* src, int64_t lds, const int32_t* ids, int32_t n, int32_t width, void* dst,
                      int64_t ldd, void* stream);
+
+/* Latent pack / unpack either side of the loop: diffusers FluxKontextPipeline._pack_latents / _unpack_latents as the
+ * reference calls them (RegionE/FluxKontext/inplace.py:212-226 via prepare_latents, :398). latents: bf16
+ * [batch, channels, height, width] (height, width even); packed: bf16 [batch, (height/2)*(width/2), 4*channels] with
+ * packed channel = 4*c + 2*dy + dx. */
+int rge_pack_latents(const void* latents, void* packed, int32_t batch, int32_t channels, int32_t height,
+                     int32_t width, void* stream);
+int rge_unpack_latents(const void* packed, void* latents, int32_t batch, int32_t channels, int32_t height,
+                       int32_t width, void* stream);
 
 /* Scheduler step (inplace.py:610-686): x' = bf16(float(x) + bf16(dt_row * v)), dt_row = edited_mask ?
  * (edited_mask[m] ? dt : dt_direct) : dt. With reuse_on != 0 the velocity is the velocity-decay cache reuse

@@ -20,7 +20,7 @@ def cosine_similarity_map(estimate: torch.Tensor, condition: torch.Tensor) -> to
 def erode_cross3(mask: torch.Tensor) -> torch.Tensor:
     """utils.py:150-181 with the 3x3 cross of :138-143: a cell survives iff it and its 4 neighbours are set; zero
     padding, so border cells never survive."""
-    k = torch.zeros(1, 1, 3, 3)
+    k = torch.zeros(1, 1, 3, 3, device=mask.device)
     k[0, 0, 1, :] = 1
     k[0, 0, :, 1] = 1
     hits = F.conv2d(mask.float()[None, None], k, padding=1)
@@ -29,7 +29,7 @@ def erode_cross3(mask: torch.Tensor) -> torch.Tensor:
 
 def dilate_square5(mask: torch.Tensor) -> torch.Tensor:
     """utils.py:184-212 with the 5x5 all-ones element (:229): a cell is set iff any cell of its 5x5 window is."""
-    hits = F.conv2d(mask.float()[None, None], torch.ones(1, 1, 5, 5), padding=2)
+    hits = F.conv2d(mask.float()[None, None], torch.ones(1, 1, 5, 5, device=mask.device), padding=2)
     return (hits > 0).float()[0, 0]
 
 
@@ -48,7 +48,7 @@ def select_tokens(estimate, condition, threshold, grid_h, grid_w, erosion_dilati
         grid = raw.float().squeeze().reshape(grid_h, grid_w)          # :337-340 (row-major token grid)
         final = clean_mask(grid).bool().flatten().unsqueeze(0)        # :342-343
     L = estimate.shape[1]
-    all_ids = torch.arange(L).unsqueeze(0)
+    all_ids = torch.arange(L, device=estimate.device).unsqueeze(0)
     edited = all_ids[final].unsqueeze(0)                              # :346-347
     unedited = all_ids[~final].view(1, L - edited.shape[1])           # :351-352
     return edited, unedited, raw, final, sim

@@ -95,6 +95,8 @@ PROTOTYPES = {
     "rge_op_rope_table": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p]),
     "rge_gather_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "rge_scatter_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "rge_pack_latents": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "rge_unpack_latents": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "rge_euler": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p, c_int32,
                             c_float, c_void_p]),
     "rge_partition": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int32,
@@ -141,7 +143,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rge_abi_version() != 2:
+    if lib.rge_abi_version() != 3:
         raise RegionEB200Error("regione_b200: ABI version mismatch")
     _LIB = lib
     return lib

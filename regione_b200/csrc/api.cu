@@ -25,7 +25,7 @@ std::atomic<long long> g_launches{0};
 
 // Optional per-class timing (bench.py's roofline): CUDA events around every GEMM / attention launch of the engine.
 enum { PC_GEMM = 0, PC_ATTN = 1, PC_NCLS = 2 };
-struct ProfRec { int cls; double work; cudaEvent_t a, b; };
+struct ProfRec { int cls; double work; cudaEvent_t a, b; int m, n, k; };
 bool g_prof = false;
 cudaEvent_t g_base = nullptr;
 std::vector<ProfRec> g_recs;
@@ -37,12 +37,17 @@ cudaEvent_t prof_event() {
   return e;
 }
 struct ProfScope {
-  cudaStream_t st; int cls; double work; cudaEvent_t a;
-  ProfScope(cudaStream_t s, int c, double w) : st(s), cls(c), work(w), a(nullptr) {
+  cudaStream_t st; int cls; double work; cudaEvent_t a; int m, n, k;
+  ProfScope(cudaStream_t s, int c, double w, int m_ = 0, int n_ = 0, int k_ = 0)
+      : st(s), cls(c), work(w), a(nullptr), m(m_), n(n_), k(k_) {
     if (g_prof) { a = prof_event(); cudaEventRecord(a, st); }
   }
   ~ProfScope() {
-    if (a) { cudaEvent_t b = prof_event(); cudaEventRecord(b, st); g_recs.push_back(ProfRec{cls, work, a, b}); }
+    if (a) {
+      cudaEvent_t b = prof_event();
+      cudaEventRecord(b, st);
+      g_recs.push_back(ProfRec{cls, work, a, b, m, n, k});
+    }
   }
 };
 
@@ -116,10 +121,15 @@ int rge_profile_collect(double* ms_busy, double* ms_sum, double* work, int64_t* 
   RGE_CUDA(cudaDeviceSynchronize());
   std::vector<std::pair<float, float>> iv[PC_NCLS];
   for (int c = 0; c < PC_NCLS; ++c) { ms_busy[c] = 0; ms_sum[c] = 0; work[c] = 0; count[c] = 0; }
+  // RGE_PROFILE_DUMP=<file>: append one line per launch (class, stream-ready ms, end ms, M/Sq, N/Skv, K/H) - the
+  // timeline used to tune the side-stream fan-out (there is no nsys in this image)
+  FILE* dump = nullptr;
+  if (const char* path = getenv("RGE_PROFILE_DUMP")) dump = fopen(path, "a");
   for (const ProfRec& r : g_recs) {
     float t0 = 0.f, t1 = 0.f;
     if (g_base && cudaEventElapsedTime(&t0, g_base, r.a) == cudaSuccess &&
         cudaEventElapsedTime(&t1, g_base, r.b) == cudaSuccess) {
+      if (dump) fprintf(dump, "%d %.4f %.4f %d %d %d\n", r.cls, t0, t1, r.m, r.n, r.k);
       iv[r.cls].push_back({t0, t1});
       ms_sum[r.cls] += t1 - t0;
       work[r.cls] += r.work;
@@ -128,6 +138,7 @@ int rge_profile_collect(double* ms_busy, double* ms_sum, double* work, int64_t* 
     g_pool.push_back(r.a);
     g_pool.push_back(r.b);
   }
+  if (dump) { fprintf(dump, "# end of collect\n"); fclose(dump); }
   g_recs.clear();
   // launches of one class overlap on the side streams: the class is "busy" over the union of its intervals
   for (int c = 0; c < PC_NCLS; ++c) {
@@ -227,6 +238,23 @@ int rge_scatter_rows(const void* src, int64_t lds, const int32_t* ids, int32_t n
   return RGE_OK;
 }
 
+int rge_pack_latents(const void* latents, void* packed, int32_t batch, int32_t channels, int32_t height,
+                     int32_t width, void* stream) {
+  if (batch > 0 && (!latents || !packed)) return fail(RGE_ERR_INVALID, "rge_pack_latents: null operand");
+  if ((height | width) & 1) return fail(RGE_ERR_INVALID, "rge_pack_latents: height and width must be even");
+  RGE_LAUNCH(launch_pack_latents((const bf16*)latents, (bf16*)packed, batch, channels, height, width, false,
+                                 (cudaStream_t)stream));
+  return RGE_OK;
+}
+int rge_unpack_latents(const void* packed, void* latents, int32_t batch, int32_t channels, int32_t height,
+                       int32_t width, void* stream) {
+  if (batch > 0 && (!latents || !packed)) return fail(RGE_ERR_INVALID, "rge_unpack_latents: null operand");
+  if ((height | width) & 1) return fail(RGE_ERR_INVALID, "rge_unpack_latents: height and width must be even");
+  RGE_LAUNCH(launch_pack_latents((const bf16*)packed, (bf16*)latents, batch, channels, height, width, true,
+                                 (cudaStream_t)stream));
+  return RGE_OK;
+}
+
 int rge_euler(const void* x, const void* v, void* out, int32_t M, int32_t channels, float dt, float dt_direct,
               const uint8_t* edited_mask, int32_t reuse_on, float ratio, void* stream) {
   if (M > 0 && (!x || !v || !out)) return fail(RGE_ERR_INVALID, "rge_euler: null operand");
@@ -278,6 +306,13 @@ struct rge_handle {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_main = nullptr, ev_aux[3] = {nullptr, nullptr, nullptr};
   bool fanout = true;
+  // REGION steps: the attention grid (query-tile pairs x heads) rarely fills a whole number of waves of the SMs. In
+  // the single-stream blocks the MLP-up GEMM is independent of attention, so attention runs on a high-priority stream
+  // (its CTAs are placed first) and the GEMM, gated on the same events and capped to the SMs the last attention wave
+  // leaves idle, runs beside it instead of in front of it.
+  cudaStream_t sattn = nullptr;
+  cudaEvent_t ev_attn = nullptr, ev_q = nullptr;
+  bool fill_attn_tail = true;
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
@@ -297,15 +332,15 @@ cudaError_t dalloc(T** p, size_t count) {
 int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bias, int N,
          int epi, bf16* out, long ldo, const int* row_map, int row_off, int col_off, const bf16* gate = nullptr,
          const bf16* res = nullptr, long ldr = 0, const bf16* norm_w = nullptr, const float2* rope = nullptr,
-         const int* rope_map = nullptr, int rope_off = 0) {
+         const int* rope_map = nullptr, int rope_off = 0, int sm_cap = 0) {
   GemmArgs a;
   a.A = A; a.lda = lda; a.M = M; a.K = K; a.W = W; a.ldw = K; a.N = N; a.bias = bias; a.epilogue = epi;
   a.out = out; a.ldo = ldo; a.row_map = row_map; a.row_off = row_off; a.col_off = col_off;
   a.gate = gate; a.res = res; a.ldr = ldr; a.norm_w = norm_w; a.rope_cs = rope; a.rope_map = rope_map;
   a.rope_off = rope_off;
   if (M <= 0) return RGE_OK;
-  ProfScope prof(st, PC_GEMM, 2.0 * M * (double)N * K);
-  RGE_LAUNCH(launch_gemm(a, h->num_sms, st));
+  ProfScope prof(st, PC_GEMM, 2.0 * M * (double)N * K, M, N, K);
+  RGE_LAUNCH(launch_gemm(a, sm_cap > 0 ? sm_cap : h->num_sms, st));
   return RGE_OK;
 }
 
@@ -368,7 +403,15 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
     A(cudaEventCreateWithFlags(&h->ev_aux[i], cudaEventDisableTiming));
   }
   A(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  {
+    int least = 0, greatest = 0;
+    A(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    A(cudaStreamCreateWithPriority(&h->sattn, cudaStreamNonBlocking, greatest));
+    A(cudaEventCreateWithFlags(&h->ev_attn, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
+  }
   if (const char* env = getenv("RGE_NO_FANOUT")) h->fanout = env[0] == '0' || env[0] == 0;
+  if (const char* env = getenv("RGE_FILL_ATTN_TAIL")) h->fill_attn_tail = env[0] != '0';
   if (e != cudaSuccess) {
     rge_destroy(h);
     return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));
@@ -392,6 +435,9 @@ int rge_destroy(rge_handle* h) {
     if (h->ev_aux[i]) cudaEventDestroy(h->ev_aux[i]);
   }
   if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->sattn) cudaStreamDestroy(h->sattn);
+  if (h->ev_attn) cudaEventDestroy(h->ev_attn);
+  if (h->ev_q) cudaEventDestroy(h->ev_q);
   delete h;
   return RGE_OK;
 }
@@ -573,14 +619,21 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
     cudaError_t e = cudaEventRecord(ev, from);
     return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
   };
-  auto attention = [&](bf16* kc, bf16* vc) -> int {
+  auto attention = [&](bf16* kc, bf16* vc, cudaStream_t sa) -> int {
     AttnArgs at;
     at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
     at.Sq = MA; at.Skv = S; at.H = h->H;
-    ProfScope prof(st, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H);
-    RGE_LAUNCH(launch_attention(at, st));
+    ProfScope prof(sa, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H, at.Sq, at.Skv, at.H);
+    RGE_LAUNCH(launch_attention(at, sa));
     return RGE_OK;
   };
+  // SMs the last (partial) wave of the attention grid leaves idle, and whether the single blocks' MLP-up GEMM fits
+  // into them within about one attention-CTA time (per-SM rates of the two kernels are comparable)
+  const int n_attn_ctas = ((MA + 255) / 256) * h->H;
+  const int attn_tail = n_attn_ctas % h->num_sms;
+  const int idle_sms = attn_tail ? h->num_sms - attn_tail : 0;
+  const bool fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 &&
+                         2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * 4.0 * 256.0 * S * 128.0;
   // ---- double-stream blocks: image chain on `st`, text chain on sT, joined around attention
   if (h->cfg.n_double > 0) RGE_CUDA(link(st, h->ev_main, sT));
   for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
@@ -612,7 +665,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
     RGE_CUDA(link(sT, h->ev_aux[0], st));
     RGE_CUDA(link(sK, h->ev_aux[1], st));
     RGE_CUDA(link(sV, h->ev_aux[2], st));
-    RGE_TRY(attention(kc, vc));
+    RGE_TRY(attention(kc, vc, st));
     RGE_CUDA(link(st, h->ev_main, sT));
     // out projections with gate * (.) + residual fused, then the feed-forward; each stream on its own chain
     RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
@@ -637,7 +690,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
     RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
-    RGE_CUDA(link(st, h->ev_main, sT));
+    if (!fill_tail) RGE_CUDA(link(st, h->ev_main, sT));
     RGE_CUDA(link(st, h->ev_main, sK));
     RGE_CUDA(link(st, h->ev_main, sV));
     RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
@@ -646,13 +699,29 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
                  0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
     RGE_TRY(gemm(h, sV, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
                  0));
-    RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr,
-                 0, D));
-    RGE_CUDA(link(sK, h->ev_aux[1], st));
-    RGE_CUDA(link(sV, h->ev_aux[2], st));
-    RGE_TRY(attention(kc, vc));
-    // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT: its CTAs and
-    // the attention CTAs share the SMs, which fills the partial last wave of either kernel
+    if (!fill_tail) {
+      RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
+                   nullptr, 0, D));
+      RGE_CUDA(link(sK, h->ev_aux[1], st));
+      RGE_CUDA(link(sV, h->ev_aux[2], st));
+      RGE_TRY(attention(kc, vc, st));
+      // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT: its CTAs and
+      // the attention CTAs share the SMs, which fills the partial last wave of either kernel
+    } else {
+      // attention (high priority) and the MLP GEMM (capped to the idle SMs) both start once q, k and v are done
+      RGE_CUDA(cudaEventRecord(h->ev_q, st));
+      RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
+      RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
+      for (cudaStream_t s2 : {h->sattn, sT}) {
+        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_q, 0));
+        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[1], 0));
+        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[2], 0));
+      }
+      RGE_TRY(attention(kc, vc, h->sattn));
+      RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
+                   nullptr, 0, D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, idle_sms));
+      RGE_CUDA(link(h->sattn, h->ev_attn, st));
+    }
     RGE_CUDA(link(sT, h->ev_aux[0], st));
     RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
                  nullptr, 0, 0, g, h->h, D));

@@ -456,6 +456,33 @@ __global__ void cfg_combine_kernel(const __nv_bfloat16* __restrict__ pos, const 
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Latent pack / unpack either side of the loop (diffusers FluxKontextPipeline._pack_latents / _unpack_latents, called at
+// RegionE/FluxKontext/inplace.py:212-226 through prepare_latents and at :398): [B, C, H, W] <-> [B, (H/2)(W/2), 4C]
+// with packed channel = c*4 + dy*2 + dx. One thread moves one 2x2 patch of one channel (two 4-byte reads, one 8-byte
+// write, or the reverse); threads run along x so the planar side is coalesced.
+template <bool kUnpack>
+__global__ void pack_latents_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int C,
+                                    int H2, int W2) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * C * H2 * W2;
+  if (idx >= total) return;
+  const int x = idx % W2;
+  const int y = (idx / W2) % H2;
+  const int c = (idx / ((long)W2 * H2)) % C;
+  const int b = idx / ((long)W2 * H2 * C);
+  const long planar = (((long)b * C + c) * (2 * H2) + 2 * y) * (2 * W2) + 2 * x;      // element (b, c, 2y, 2x)
+  const long packed = (((long)b * H2 + y) * W2 + x) * (4 * C) + 4 * c;                 // token (y, x), channel 4c
+  if (!kUnpack) {
+    const uint32_t top = *reinterpret_cast<const uint32_t*>(src + planar);
+    const uint32_t bot = *reinterpret_cast<const uint32_t*>(src + planar + 2 * W2);
+    *reinterpret_cast<uint2*>(dst + packed) = make_uint2(top, bot);
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(src + packed);
+    *reinterpret_cast<uint32_t*>(dst + planar) = v.x;
+    *reinterpret_cast<uint32_t*>(dst + planar + 2 * W2) = v.y;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_ln_modulate(const __nv_bfloat16* x, long ldx, const __nv_bfloat16* scale,
@@ -528,6 +555,16 @@ cudaError_t launch_build_selection(const int* sel_img, int n_img, int T, int* se
   const int n = n_img > T ? n_img : T;
   if (n <= 0) return cudaSuccess;
   build_selection_kernel<<<cdiv(n, 256), 256, 0, s>>>(sel_img, n_img, T, sel_img_out, sel_all_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_latents(const __nv_bfloat16* src, __nv_bfloat16* dst, int B, int C, int H, int W, bool unpack,
+                                cudaStream_t s) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return cudaSuccess;
+  if ((H & 1) || (W & 1)) return cudaErrorInvalidValue;
+  const long total = (long)B * C * (H / 2) * (W / 2);
+  if (unpack) pack_latents_kernel<true><<<cdiv(total, 256), 256, 0, s>>>(src, dst, B, C, H / 2, W / 2);
+  else pack_latents_kernel<false><<<cdiv(total, 256), 256, 0, s>>>(src, dst, B, C, H / 2, W / 2);
   return cudaGetLastError();
 }
 

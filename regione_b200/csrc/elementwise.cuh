@@ -69,4 +69,8 @@ cudaError_t launch_arp_similarity(const __nv_bfloat16* x, const __nv_bfloat16* v
 cudaError_t launch_morph_compact(const uint8_t* mask_in, uint8_t* mask_out, int gh, int gw, int erosion_dilation,
                                  int* edited, int* unedited, int* counts, cudaStream_t s);
 
+// Latent pack / unpack: planar [B, C, H, W] <-> packed [B, (H/2)(W/2), 4C] (packed channel = 4c + 2dy + dx).
+cudaError_t launch_pack_latents(const __nv_bfloat16* src, __nv_bfloat16* dst, int B, int C, int H, int W, bool unpack,
+                                cudaStream_t s);
+
 }  // namespace rge

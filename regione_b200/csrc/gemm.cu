@@ -1,10 +1,10 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] @ W[N,K]^T).
 //
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128xBK / BNxBK tiles, kStages-deep ring)
-//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16, accumulators in TMEM)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128 N=bn K=16, accumulators in TMEM)
 //   warps 2-5   epilogue       (tcgen05.ld -> registers -> fused epilogue -> global), one thread per output row
 //
-// TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// TMEM holds two 256-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Replaces the reference's nn.Linear calls and its Triton scatter-GEMM `_partially_linear`
 // (RegionE/FluxKontext/fused_kernels.py:9-101): the scatter is the `row_map` of the epilogue, and the
 // per-head RMSNorm + RoPE the reference re-applies to the whole cache every step
@@ -24,37 +24,44 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 192;
+constexpr int kMaxBN = 256;                 // widest tile; TMEM holds two accumulators of this width
+constexpr int kMaxStages = 8;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kRingBytes = 4 * (kABytes + kMaxBN * BK * 2);   // 192 KB operand ring, cut into stages at run time
+constexpr int kBarBytes = 256;
+constexpr int kSmemBytes = kRingBytes + kBarBytes + 1024;     // +1024: manual alignment slack
+constexpr int kTmemCols = 2 * kMaxBN;
 
-template <int BN>
-struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
-  static constexpr int kTmemCols = 2 * BN;
+// Tile width `bn` and ring depth are launch parameters (not template parameters): region steps and the text stream
+// have few rows (M = 512 ... ~2500), where a fixed 128 x 256 tile leaves the last wave of the 148 SMs half empty;
+// the host picks the width that minimises the makespan (pick_bn below) and narrower tiles get a deeper ring.
+struct TileCfg {
+  int bn;       // multiple of 32 (of 128 for EPI_NORM_ROPE), 32 ... 256
+  int stages;   // <= kMaxStages, stages * (kABytes + bn * 128) <= kRingBytes
 };
 
-template <int BN, int EPI>
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmDev p) {
-  using C = Cfg<BN>;
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmDev p,
+            const TileCfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int bn = cfg.bn;
+  const int n_stages = cfg.stages;
+  const int stage_bytes = kABytes + bn * BK * 2;   // multiple of 1024: both operand tiles stay swizzle-aligned
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -65,7 +72,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -74,7 +81,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_m = (p.M + BM - 1) / BM;
-  const int num_n = (p.N + BN - 1) / BN;
+  const int num_n = (p.N + bn - 1) / bn;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
 
@@ -87,19 +94,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int m_blk = tile % num_m, n_blk = tile / num_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * bn);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(BM, bn, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -108,12 +115,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const uint32_t use = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], use ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + C::kABytes;
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + kABytes;
           const uint64_t a_desc = make_sdesc_sw128(sa, 0, 1024);
           const uint64_t b_desc = make_sdesc_sw128(sb, 0, 1024);
 #pragma unroll
@@ -122,7 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull_bar[acc]);
       }
@@ -138,8 +145,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const uint32_t use = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      gemm_epilogue_row<BN, EPI>(p, taddr, m_blk * BM + r, n_blk * BN);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * kMaxBN;
+      gemm_epilogue_row<EPI>(p, taddr, m_blk * BM + r, n_blk * bn, bn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -148,36 +155,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int BN, int EPI>
+// Tile width for the 1-CTA kernel: minimise  waves x (bn + fixed per-tile cost)  over the widths the epilogue allows.
+// The fixed cost (in output columns) stands for the prologue / epilogue drain of a tile and for the A-tile re-reads of
+// narrow tiles; ties go to the wider tile. RGE_GEMM_BN=<n> forces a width (tuning / tests).
+int pick_bn(const GemmArgs& a, int num_sms) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* env = getenv("RGE_GEMM_BN");
+    forced = env ? atoi(env) : 0;
+  }
+  const bool heads = a.epilogue == EPI_NORM_ROPE;
+  if (forced > 0 && forced <= kMaxBN && forced % (heads ? 128 : 32) == 0) return forced;
+  const int num_m = (a.M + BM - 1) / BM;
+  const int cand_all[] = {256, 224, 192, 160, 128, 96, 64};
+  const int cand_heads[] = {256, 128};
+  const int* cand = heads ? cand_heads : cand_all;
+  const int n_cand = heads ? 2 : 7;
+  int best = 0;
+  long best_cost = 0;
+  for (int i = 0; i < n_cand; ++i) {
+    const int bn = cand[i];
+    const long tiles = (long)num_m * ((a.N + bn - 1) / bn);
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    const long cost = waves * (bn + 32);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+template <int EPI>
 cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  TileCfg cfg;
+  cfg.bn = pick_bn(a, num_sms);
+  cfg.stages = kRingBytes / (kABytes + cfg.bn * BK * 2);
+  if (cfg.stages > kMaxStages) cfg.stages = kMaxStages;
   CUtensorMap map_a, map_b;
   if (!make_tmap_bf16_2d(&map_a, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, cfg.bn)) return cudaErrorInvalidValue;
   const GemmDev p = to_dev(a);
-  const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + cfg.bn - 1) / cfg.bn);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  gemm_kernel<BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(map_a, map_b, p);
+  gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, cfg);
   return cudaGetLastError();
 }
 
-template <int BN>
-cudaError_t launch_bn(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+cudaError_t launch_1cta(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   switch (a.epilogue) {
-    case EPI_STORE: return launch_t<BN, EPI_STORE>(a, num_sms, stream);
-    case EPI_GELU: return launch_t<BN, EPI_GELU>(a, num_sms, stream);
-    case EPI_GATE_RES: return launch_t<BN, EPI_GATE_RES>(a, num_sms, stream);
-    case EPI_NORM_ROPE: return launch_t<BN, EPI_NORM_ROPE>(a, num_sms, stream);
+    case EPI_STORE: return launch_t<EPI_STORE>(a, num_sms, stream);
+    case EPI_GELU: return launch_t<EPI_GELU>(a, num_sms, stream);
+    case EPI_GATE_RES: return launch_t<EPI_GATE_RES>(a, num_sms, stream);
+    case EPI_NORM_ROPE: return launch_t<EPI_NORM_ROPE>(a, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -202,8 +238,7 @@ cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     cudaError_t e = launch_gemm_2cta(a, num_sms, stream);
     if (e != cudaErrorNotSupported) return e;
   }
-  if (a.N % 256 == 0) return launch_bn<256>(a, num_sms, stream);
-  return launch_bn<128>(a, num_sms, stream);
+  return launch_1cta(a, num_sms, stream);
 }
 
 }  // namespace rge

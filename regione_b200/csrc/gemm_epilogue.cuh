@@ -34,9 +34,10 @@ inline GemmDev to_dev(const GemmArgs& a) {
 __device__ __forceinline__ float ldg_bf16f(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
 
 // taddr: TMEM address of this thread's row (lane field set) at column 0 of the accumulator; m: global row;
-// n_base: first global column of the tile; BN: tile width. All 32 lanes of the warp must call this together.
-template <int BN, int EPI>
-__device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t taddr, int m, int n_base) {
+// n_base: first global column of the tile; bn: tile width (multiple of 32; of 128 for EPI_NORM_ROPE). All 32 lanes of
+// the warp must call this together.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t taddr, int m, int n_base, int bn) {
   const bool valid = m < p.M;
   const long out_row = valid ? (long)((p.row_map ? __ldg(p.row_map + m) : m) + p.row_off) : 0;
   __nv_bfloat16* out_ptr = p.out + out_row * p.ldo + p.col_off;
@@ -44,7 +45,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
     const long rope_row = valid ? (long)((p.rope_map ? __ldg(p.rope_map + m) : m) + p.rope_off) : 0;
     const float2* cs_row = p.rope_cs + rope_row * 64;
 #pragma unroll 1
-    for (int h = 0; h < BN / 128; ++h) {
+    for (int h = 0; h < bn / 128; ++h) {
       const int n0 = n_base + h * 128;
       if (n0 >= p.N) break;
       float ss = 0.f;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
     }
   } else {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < bn / 32; ++c) {
       const int n0 = n_base + c * 32;
       if (n0 >= p.N) break;
       uint32_t v[32];

@@ -151,6 +151,33 @@ def scatter_rows(src, ids, dst):
     return dst
 
 
+def pack_latents(latents):
+    """[B, C, H, W] bf16 -> [B, (H/2)(W/2), 4C] (FluxKontextPipeline._pack_latents)."""
+    lib = _lib.load()
+    _req(latents, torch.bfloat16, "latents")
+    latents = latents.contiguous()
+    B, Cc, H, W = latents.shape
+    out = torch.empty(B, (H // 2) * (W // 2), 4 * Cc, dtype=torch.bfloat16, device=latents.device)
+    check(lib.rge_pack_latents(ptr(latents), ptr(out), B, Cc, H, W, stream_ptr()), "rge_pack_latents")
+    return out
+
+
+def unpack_latents(packed, height: int, width: int, vae_scale_factor: int = 8):
+    """[B, L, 4C] bf16 -> [B, C, H, W] with H = 2 * (height // (2 * vae_scale_factor)), likewise W
+    (FluxKontextPipeline._unpack_latents; `height` / `width` are in pixels)."""
+    lib = _lib.load()
+    _req(packed, torch.bfloat16, "packed")
+    packed = packed.contiguous()
+    B, L, ch = packed.shape
+    H = 2 * (int(height) // (vae_scale_factor * 2))
+    W = 2 * (int(width) // (vae_scale_factor * 2))
+    if L != (H // 2) * (W // 2) or ch % 4:
+        raise _lib.RegionEB200Error(f"unpack_latents: {L} tokens x {ch} channels do not match {height} x {width}")
+    out = torch.empty(B, ch // 4, H, W, dtype=torch.bfloat16, device=packed.device)
+    check(lib.rge_unpack_latents(ptr(packed), ptr(out), B, ch // 4, H, W, stream_ptr()), "rge_unpack_latents")
+    return out
+
+
 def euler(x, v, dt: float, dt_direct: float = 0.0, edited_mask=None, reuse_ratio: float | None = None, out=None):
     lib = _lib.load()
     _req(x, torch.bfloat16, "x"); _req(v, torch.bfloat16, "v")

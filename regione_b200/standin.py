@@ -224,6 +224,22 @@ class FluxKontextPipeline:
     def joint_attention_kwargs(self):
         return self._joint_attention_kwargs
 
+    # latent <-> token layout either side of the loop (diffusers FluxKontextPipeline statics the reference calls through
+    # prepare_latents and at inplace.py:398), on the CUDA library's pack kernels
+    @staticmethod
+    def _pack_latents(latents, batch_size=None, num_channels_latents=None, height=None, width=None):
+        from . import ops
+        return ops.pack_latents(latents)
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor):
+        from . import ops
+        return ops.unpack_latents(latents, height, width, vae_scale_factor)
+
+    @staticmethod
+    def _prepare_latent_image_ids(batch_size, height, width, device, dtype):
+        return latent_image_ids(height, width, 0.0, device, dtype)
+
     def __call__(self, *args, **kwargs):
         raise NotImplementedError(
             "vanilla FluxKontextPipeline.__call__ is diffusers code; enable RegionE first: "

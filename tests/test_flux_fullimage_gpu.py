@@ -1,0 +1,58 @@
+"""configs[1] end to end: one complete 28-step RegionE denoise at the BASELINE shapes (FLUX.1-Kontext 1024^2: T=512,
+L=C=4096, D=3072, 24 heads, 19 + 38 blocks) through RegionEHelper / the C ABI against the oracle at the same size and
+depth (the oracle runs on the GPU box's device as the checker, with its exact fp32-softmax attention). Gates
+(north_star): identical step schedule, region mask bit-exact, relative L2 of the bf16 latents <= 1e-2 at every step."""
+import pytest
+import torch
+
+from oracle.flux import FluxOracle
+from oracle.loop import run_regione
+from oracle.schedule import GAMMA
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def test_whole_image_at_baseline_shapes_and_depth():
+    from regione_b200 import RegionEHelper
+    from regione_b200 import synthetic as syn
+    from regione_b200.standin import latent_image_ids
+
+    dev = "cuda"
+    arch, G, T = syn.FLUX_KONTEXT, 64, 512
+    params = dict(warmup_step=6, post_step=2, refresh_step="16", threshold=0.88, cache_threshold=0.04,
+                  erosion_dilation=True)
+    pipe = syn.build_pipeline(arch, seed=110, device=dev)
+    w = {k: v.detach() for k, v in pipe.transformer.state_dict().items()}
+    inp = syn.make_inputs(110, G, G, T, arch["ctx_dim"], arch["pooled_dim"], rho=0.25, device=dev)
+    ids = torch.cat([latent_image_ids(G, G, 0.0, dev), latent_image_ids(G, G, 1.0, dev)])
+    with torch.no_grad():
+        ref, ref_tr = run_regione(FluxOracle(w, arch["heads"], arch["n_double"], arch["n_single"], True),
+                                  dict(num_inference_steps=28, **params), GAMMA["FluxKontext"], inp["latents"],
+                                  inp["image_latents"], ids, torch.zeros(T, 3, device=dev), inp["prompt_embeds"],
+                                  inp["pooled_prompt_embeds"], 2.5, inp["height"], inp["width"], record=True)
+    helper = RegionEHelper(pipe)
+    helper.set_params(**params)
+    helper.enable()
+    try:
+        p = helper.pipeline
+        p.regione_record = True
+        kw = {k: v for k, v in inp.items() if k != "intended_mask"}
+        out = p(guidance_scale=2.5, num_inference_steps=28, output_type="latent", return_dict=False, **kw)[0]
+        torch.cuda.synchronize()
+        tr = p.regione_trace
+    finally:
+        helper.disable()
+    assert tr["modes"] == ref_tr["modes"]
+    assert tr["modes"].count("FULL") == 9 and tr["modes"].count("REGION") == 5
+    assert torch.equal(tr["edited_ids"], ref_tr["edited_ids"].squeeze(0).to(torch.int32)), "region mask differs"
+    assert 600 < tr["edited_ids"].numel() < 1600
+    worst_v = max(rel_l2(a, b[0]) for a, b, m in zip(tr["noise_pred"], ref_tr["noise_pred"], tr["modes"]) if m != "SKIP")
+    worst_x = max(rel_l2(a, b[0]) for a, b in zip(tr["latents"], ref_tr["latents"]))
+    print(f"configs[1] whole image: edited {tr['edited_ids'].numel()}, worst velocity rel-L2 {worst_v:.3e}, "
+          f"worst latent rel-L2 {worst_x:.3e}, final {rel_l2(out, ref):.3e}")
+    assert worst_x <= 1e-2 and rel_l2(out, ref) <= 1e-2

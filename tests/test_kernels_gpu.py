@@ -74,6 +74,48 @@ def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
         assert rel_l2(q, x.transpose(1, 2).reshape(M, N)) <= BF16_TOL
 
 
+# (M, N) chosen so that the 1-CTA kernel's tile-width heuristic (gemm.cu pick_bn, 148 SMs) lands on every width it
+# can choose: 1576x3072 -> 160, 512x3072 -> 96, 1064x3072 -> 192, 1576x12288 -> 224, 716x3072 -> 128, 300x64 -> 64,
+# 100x3104 (ragged last tile) -> 64, 1900x1536 -> 96/128; K ragged too.
+@pytest.mark.parametrize("M,N,K", [(1576, 3072, 320), (512, 3072, 256), (1064, 3072, 192), (1576, 12288, 128),
+                                   (716, 3072, 456), (300, 64, 3072), (100, 3104, 64), (1900, 1536, 200)])
+def test_gemm_region_step_tile_widths_all_epilogues(M, N, K):
+    from regione_b200 import _lib, ops
+    g = _gen(31)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    lin = F.linear(a, w, b)
+    assert rel_l2(ops.gemm(a, w, b), a.float() @ w.float().t() + b.float()) <= BF16_TOL
+    assert rel_l2(ops.gemm(a, w, b, epilogue=_lib.EPI_GELU), F.gelu(lin, approximate="tanh")) <= BF16_TOL
+    gate = torch.randn(N, device="cuda", generator=g).bfloat16()
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = res.clone()
+    ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, gate=gate, res=out, out=out)
+    assert rel_l2(out, res + gate[None] * lin) <= BF16_TOL
+    # scatter into a wider buffer at a column offset: rows / columns outside the target stay untouched
+    S = M + 50
+    rows = torch.randperm(S, device="cuda", generator=g)[:M]
+    wide = torch.full((S, N + 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, b, out=wide, row_map=rows.int(), col_off=32)
+    assert rel_l2(wide[rows, 32:32 + N], lin) <= BF16_TOL
+    assert bool((wide[:, :32] == 7).all()) and bool((wide[:, 32 + N:] == 7).all())
+    keep = torch.ones(S, dtype=torch.bool, device="cuda")
+    keep[rows] = False
+    assert bool((wide[keep] == 7).all())
+    if N % 128 == 0:
+        H = N // 128
+        nw = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
+        ids = torch.zeros(S, 3, device="cuda")
+        ids[:, 1] = torch.arange(S, device="cuda") // 64
+        ids[:, 2] = torch.arange(S, device="cuda") % 64
+        cs = ops.rope_table(ids)
+        cos, sin = of.rope_cos_sin(ids)
+        q = ops.gemm(a, w, b, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=rows.int())
+        x = of.apply_rope(of.rms_norm(lin.view(1, M, H, 128).transpose(1, 2), nw), (cos[rows], sin[rows]))
+        assert rel_l2(q, x.transpose(1, 2).reshape(M, N)) <= BF16_TOL
+
+
 def test_gemm_fused_epilogues():
     from regione_b200 import _lib, ops
     g = _gen(2)
@@ -266,3 +308,18 @@ def test_full_size_properties():
     out2, ed2, _ = ops.compact(out, 64, 64, False)
     assert torch.equal(out2, out) and torch.equal(ed2, ed)                                # compaction is idempotent
     assert torch.equal(ops.euler(x, x, 0.0), x)                                           # dt = 0 is the identity
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 16, 128, 128), (2, 16, 100, 162), (1, 4, 2, 2), (3, 16, 96, 96)])
+def test_pack_unpack_latents_bit_exact(B, C, H, W):
+    """diffusers _pack_latents / _unpack_latents (view / permute / reshape) restated in torch as the checker."""
+    from regione_b200 import ops
+    x = torch.randn(B, C, H, W, device="cuda", generator=_gen(41)).bfloat16()
+    ref = x.view(B, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // 2) * (W // 2), C * 4)
+    got = ops.pack_latents(x)
+    assert torch.equal(got, ref)
+    back = ops.unpack_latents(got, H * 8, W * 8, 8)
+    ref_back = ref.view(B, H // 2, W // 2, C, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, C, H, W)
+    assert torch.equal(back, ref_back) and torch.equal(back, x)
+    from regione_b200.standin import FluxKontextPipeline
+    assert torch.equal(FluxKontextPipeline._unpack_latents(FluxKontextPipeline._pack_latents(x), H * 8, W * 8, 8), x)
