@@ -136,6 +136,75 @@ __global__ void __launch_bounds__(256) ln_modulate_reg_kernel(const __nv_bfloat1
   }
 }
 
+// Wide rows (D = 1024 * NV, e.g. 3072): four warps share one row, two rows per 256-thread block. Each thread keeps NV
+// 128-bit vectors (12 registers at NV = 3), the mean / variance cross the four warps through shared memory, and the
+// block stays below 64 registers per thread so that 4+ blocks (32+ warps) are resident per SM: the one-warp-per-row
+// variant above needs the whole row plus its scale / shift vectors in one thread's registers (255 at D = 3072, one
+// block per SM) and ran at a third of the HBM rate.
+template <int NV>
+__global__ void __launch_bounds__(256, 4) ln_modulate_wide_kernel(const __nv_bfloat16* __restrict__ x, long ldx,
+                                                                  const __nv_bfloat16* __restrict__ scale,
+                                                                  const __nv_bfloat16* __restrict__ shift,
+                                                                  __nv_bfloat16* __restrict__ out, long ldo, int M) {
+  constexpr int D = 1024 * NV;
+  __shared__ float red[2][2][4];                 // [pass][row in block][warp of the row]
+  const int t = threadIdx.x & 127;               // thread within the row
+  const int rb = threadIdx.x >> 7;               // row within the block
+  const int w = (threadIdx.x >> 5) & 3;
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 2 + rb;
+  const bool live = m < M;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long)(live ? m : 0) * ldx);
+  uint4 r[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r[i] = live ? xr[t + 128 * i] : make_uint4(0, 0, 0, 0);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(r[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[0][rb][w] = s;
+  __syncthreads();
+  const float mean = ((red[0][rb][0] + red[0][rb][1]) + (red[0][rb][2] + red[0][rb][3])) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8];
+    unpack8(r[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = f[j] - mean;
+      q += d * d;
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) red[1][rb][w] = q;
+  __syncthreads();
+  const float rstd = rsqrtf(((red[1][rb][0] + red[1][rb][1]) + (red[1][rb][2] + red[1][rb][3])) * (1.0f / D) + 1e-6f);
+  if (!live) return;
+  const uint4* sc = reinterpret_cast<const uint4*>(scale);
+  const uint4* sh = reinterpret_cast<const uint4*>(shift);
+  uint4* o = reinterpret_cast<uint4*>(out + (long)m * ldo);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float f[8], a[8], b[8];
+    unpack8(r[i], f);
+    unpack8(__ldg(sc + t + 128 * i), a);
+    unpack8(__ldg(sh + t + 128 * i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float n = bf16_round((f[j] - mean) * rstd);
+      const float tt = bf16_round(n * bf16_round(1.0f + a[j]));
+      f[j] = tt + b[j];
+    }
+    o[t + 128 * i] = pack8(f);
+  }
+}
+
 // ------------------------------------------------------------------ batched GEMV
 __global__ void __launch_bounds__(256) gemv_batch_kernel(const GemvJob* __restrict__ jobs) {
   extern __shared__ float xs[];
@@ -244,41 +313,51 @@ __global__ void euler_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfl
 }
 
 // ------------------------------------------------------------------ adaptive region partition (utils.py:305-333)
-// One warp per token; warp-shuffle reductions over the channel axis.
+// kLanes = channels / 8 lanes own one token (one 128-bit load per tensor per lane, 32 / kLanes tokens per warp);
+// reductions over the channel axis are shuffles inside the lane group.
+template <int kLanes>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = kLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int kLanes>
 __global__ void __launch_bounds__(256) arp_similarity_kernel(const __nv_bfloat16* __restrict__ x,
                                                              const __nv_bfloat16* __restrict__ v,
                                                              const __nv_bfloat16* __restrict__ cond, float dt_final,
                                                              float thr, uint8_t* __restrict__ mask,
-                                                             float* __restrict__ sim_out, int L, int Cch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + warp;
-  if (m >= L) return;
-  float e[4], c[4];
+                                                             float* __restrict__ sim_out, int L) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one (token, 8-channel vector) per thread
+  const long m = idx / kLanes;
+  const bool live = m < L;
+  float e[8], c[8], xf[8], vf[8];
+  if (live) {
+    unpack8(reinterpret_cast<const uint4*>(x)[idx], xf);
+    unpack8(reinterpret_cast<const uint4*>(v)[idx], vf);
+    unpack8(reinterpret_cast<const uint4*>(cond)[idx], c);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xf[j] = vf[j] = c[j] = 0.f;
+  }
   float ss_e = 0.f, ss_c = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ch = lane + 32 * i;
-    e[i] = 0.f;
-    c[i] = 0.f;
-    if (ch < Cch) {
-      const long o = (long)m * Cch + ch;
-      // one-step x0 estimate, fp32: sample + bf16(dt_final * model_output)   (inplace.py:650)
-      e[i] = __bfloat162float(x[o]) + bf16_round(dt_final * __bfloat162float(v[o]));
-      c[i] = __bfloat162float(cond[o]);
-      ss_e += e[i] * e[i];
-      ss_c += c[i] * c[i];
-    }
+  for (int j = 0; j < 8; ++j) {
+    // one-step x0 estimate, fp32: sample + bf16(dt_final * model_output)   (inplace.py:650)
+    e[j] = xf[j] + bf16_round(dt_final * vf[j]);
+    ss_e += e[j] * e[j];
+    ss_c += c[j] * c[j];
   }
-  ss_e = warp_sum(ss_e);
-  ss_c = warp_sum(ss_c);
+  ss_e = group_sum<kLanes>(ss_e);
+  ss_c = group_sum<kLanes>(ss_c);
   // F.normalize: fp32 tensor in fp32; the bf16 condition latent in bf16 (norm rounded to bf16, quotient too)
   const float den_e = fmaxf(sqrtf(ss_e), 1e-12f);
   const float den_c = fmaxf(bf16_round(sqrtf(ss_c)), bf16_round(1e-12f));
   float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dot += (e[i] / den_e) * bf16_round(c[i] / den_c);
-  dot = warp_sum(dot);
-  if (lane == 0) {
+  for (int j = 0; j < 8; ++j) dot += (e[j] / den_e) * bf16_round(c[j] / den_c);
+  dot = group_sum<kLanes>(dot);
+  if (live && (threadIdx.x % kLanes) == 0) {
     mask[m] = dot <= thr ? 1 : 0;
     if (sim_out) sim_out[m] = dot;
   }
@@ -395,63 +474,78 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __res
 // ------------------------------------------------------------------ norm-rescaled classifier-free guidance
 // RegionE/QwenImageEdit/inplace.py:386-405: comb = neg + s * (pos - neg); out = comb * (||pos|| / ||comb||), every
 // intermediate a bf16 tensor (row norms accumulate in fp32 and round to bf16). One warp per token.
+template <int kLanes>
 __global__ void __launch_bounds__(256) cfg_rescale_kernel(const __nv_bfloat16* __restrict__ pos,
                                                           const __nv_bfloat16* __restrict__ neg, float scale,
-                                                          __nv_bfloat16* __restrict__ out, int M, int Cch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + warp;
-  if (m >= M) return;
-  float comb[4];
+                                                          __nv_bfloat16* __restrict__ out, int M) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one (token, 8-channel vector) per thread
+  const bool live = idx / kLanes < M;
+  float p[8], n[8], comb[8];
+  if (live) {
+    unpack8(reinterpret_cast<const uint4*>(pos)[idx], p);
+    unpack8(reinterpret_cast<const uint4*>(neg)[idx], n);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { p[j] = 0.f; n[j] = 0.f; }
+  }
   float sp = 0.f, sc = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ch = lane + 32 * i;
-    comb[i] = 0.f;
-    if (ch < Cch) {
-      const long o = (long)m * Cch + ch;
-      const float p = __bfloat162float(pos[o]), n = __bfloat162float(neg[o]);
-      comb[i] = bf16_round(n + bf16_round(scale * bf16_round(p - n)));
-      sp += p * p;
-      sc += comb[i] * comb[i];
-    }
+  for (int j = 0; j < 8; ++j) {
+    comb[j] = bf16_round(n[j] + bf16_round(scale * bf16_round(p[j] - n[j])));
+    sp += p[j] * p[j];
+    sc += comb[j] * comb[j];
   }
-  const float cond_norm = bf16_round(sqrtf(warp_sum(sp)));
-  const float noise_norm = bf16_round(sqrtf(warp_sum(sc)));
+  const float cond_norm = bf16_round(sqrtf(group_sum<kLanes>(sp)));
+  const float noise_norm = bf16_round(sqrtf(group_sum<kLanes>(sc)));
   const float r = bf16_round(cond_norm / noise_norm);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ch = lane + 32 * i;
-    if (ch < Cch) out[(long)m * Cch + ch] = __float2bfloat16_rn(comb[i] * r);
-  }
+  for (int j = 0; j < 8; ++j) comb[j] *= r;
+  if (live) reinterpret_cast<uint4*>(out)[idx] = pack8(comb);
 }
 
 // ------------------------------------------------------------------ Step1X classifier-free guidance pieces
 // RegionE/Step1XEdit/inplace.py:388-400: diff_norm = ||pos - neg|| per token (bf16), then
 // out = neg + scale * (pos - neg) [/ denom], every intermediate a bf16 tensor. One warp per token.
+template <int kLanes>
 __global__ void __launch_bounds__(256) row_diff_norm_kernel(const __nv_bfloat16* __restrict__ pos,
                                                             const __nv_bfloat16* __restrict__ neg,
-                                                            __nv_bfloat16* __restrict__ out, int M, int Cch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + warp;
-  if (m >= M) return;
+                                                            __nv_bfloat16* __restrict__ out, int M) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one (token, 8-channel vector) per thread
+  const long m = idx / kLanes;
+  const bool live = m < M;
+  float p[8], n[8];
+  if (live) {
+    unpack8(reinterpret_cast<const uint4*>(pos)[idx], p);
+    unpack8(reinterpret_cast<const uint4*>(neg)[idx], n);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { p[j] = 0.f; n[j] = 0.f; }
+  }
   float ss = 0.f;
-  for (int ch = lane; ch < Cch; ch += 32) {
-    const long o = (long)m * Cch + ch;
-    const float d = bf16_round(__bfloat162float(pos[o]) - __bfloat162float(neg[o]));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float d = bf16_round(p[j] - n[j]);
     ss += d * d;
   }
-  ss = warp_sum(ss);
-  if (lane == 0) out[m] = __float2bfloat16_rn(sqrtf(ss));
+  ss = group_sum<kLanes>(ss);
+  if (live && (threadIdx.x % kLanes) == 0) out[m] = __float2bfloat16_rn(sqrtf(ss));
 }
 __global__ void cfg_combine_kernel(const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ neg,
                                    float scale, const __nv_bfloat16* __restrict__ denom,
-                                   __nv_bfloat16* __restrict__ out, int M, int Cch) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)M * Cch) return;
-  const float p = __bfloat162float(pos[idx]), n = __bfloat162float(neg[idx]);
-  float e = bf16_round(scale * bf16_round(p - n));
-  if (denom) e = bf16_round(e / __bfloat162float(denom[idx / Cch]));
-  out[idx] = __float2bfloat16_rn(n + e);
+                                   __nv_bfloat16* __restrict__ out, int M, int vec_per_row) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-channel vector per thread
+  if (idx >= (long)M * vec_per_row) return;
+  float p[8], n[8];
+  unpack8(reinterpret_cast<const uint4*>(pos)[idx], p);
+  unpack8(reinterpret_cast<const uint4*>(neg)[idx], n);
+  const float den = denom ? __bfloat162float(denom[idx / vec_per_row]) : 1.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float e = bf16_round(scale * bf16_round(p[j] - n[j]));
+    if (denom) e = bf16_round(e / den);
+    n[j] += e;
+  }
+  reinterpret_cast<uint4*>(out)[idx] = pack8(n);
 }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
@@ -490,7 +584,9 @@ cudaError_t launch_ln_modulate(const __nv_bfloat16* x, long ldx, const __nv_bflo
                                cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
   if (D % 8 || ldx % 8 || ldo % 8) return cudaErrorInvalidValue;
-  if (D == 3072) ln_modulate_reg_kernel<12><<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
+  if (D == 3072) ln_modulate_wide_kernel<3><<<cdiv(M, 2), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
+  else if (D == 2048) ln_modulate_wide_kernel<2><<<cdiv(M, 2), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
+  else if (D == 4096) ln_modulate_wide_kernel<4><<<cdiv(M, 2), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
   else if (D == 256) ln_modulate_reg_kernel<1><<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M);
   else ln_modulate_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ldx, scale, shift, out, ldo, M, D);
   return cudaGetLastError();
@@ -507,22 +603,34 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long ldx, const __nv_bfloat16
 cudaError_t launch_cfg_rescale(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale, __nv_bfloat16* out,
                                int M, int Cch, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
-  if (Cch > 128) return cudaErrorInvalidValue;
-  cfg_rescale_kernel<<<cdiv(M, 8), 256, 0, s>>>(pos, neg, scale, out, M, Cch);
+  const int grid = cdiv((long)M * (Cch / 8), 256);
+  switch (Cch) {   // lanes per token = channels / 8 must be a power of two (the reference packs 64 channels)
+    case 32: cfg_rescale_kernel<4><<<grid, 256, 0, s>>>(pos, neg, scale, out, M); break;
+    case 64: cfg_rescale_kernel<8><<<grid, 256, 0, s>>>(pos, neg, scale, out, M); break;
+    case 128: cfg_rescale_kernel<16><<<grid, 256, 0, s>>>(pos, neg, scale, out, M); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_row_diff_norm(const __nv_bfloat16* pos, const __nv_bfloat16* neg, __nv_bfloat16* out, int M,
                                  int Cch, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
-  row_diff_norm_kernel<<<cdiv(M, 8), 256, 0, s>>>(pos, neg, out, M, Cch);
+  const int grid = cdiv((long)M * (Cch / 8), 256);
+  switch (Cch) {
+    case 32: row_diff_norm_kernel<4><<<grid, 256, 0, s>>>(pos, neg, out, M); break;
+    case 64: row_diff_norm_kernel<8><<<grid, 256, 0, s>>>(pos, neg, out, M); break;
+    case 128: row_diff_norm_kernel<16><<<grid, 256, 0, s>>>(pos, neg, out, M); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_cfg_combine(const __nv_bfloat16* pos, const __nv_bfloat16* neg, float scale,
                                const __nv_bfloat16* denom, __nv_bfloat16* out, int M, int Cch, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
-  cfg_combine_kernel<<<cdiv((long)M * Cch, 256), 256, 0, s>>>(pos, neg, scale, denom, out, M, Cch);
+  if (Cch % 8) return cudaErrorInvalidValue;
+  cfg_combine_kernel<<<cdiv((long)M * (Cch / 8), 256), 256, 0, s>>>(pos, neg, scale, denom, out, M, Cch / 8);
   return cudaGetLastError();
 }
 
@@ -597,8 +705,13 @@ cudaError_t launch_arp_similarity(const __nv_bfloat16* x, const __nv_bfloat16* v
                                   float dt_final, float thr, uint8_t* mask, float* sim_out, int L, int Cch,
                                   cudaStream_t s) {
   if (L <= 0) return cudaSuccess;
-  if (Cch > 128) return cudaErrorInvalidValue;
-  arp_similarity_kernel<<<cdiv(L, 8), 256, 0, s>>>(x, v, cond, dt_final, thr, mask, sim_out, L, Cch);
+  const int grid = cdiv((long)L * (Cch / 8), 256);
+  switch (Cch) {   // lanes per token = channels / 8 must be a power of two (the reference packs 64 channels)
+    case 32: arp_similarity_kernel<4><<<grid, 256, 0, s>>>(x, v, cond, dt_final, thr, mask, sim_out, L); break;
+    case 64: arp_similarity_kernel<8><<<grid, 256, 0, s>>>(x, v, cond, dt_final, thr, mask, sim_out, L); break;
+    case 128: arp_similarity_kernel<16><<<grid, 256, 0, s>>>(x, v, cond, dt_final, thr, mask, sim_out, L); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

@@ -213,7 +213,7 @@ def test_attention_strided_output_and_row_independence():
 def test_ln_modulate_matches_oracle():
     from regione_b200 import ops
     g = _gen(7)
-    for M, D in [(517, 3072), (3, 256), (64, 768)]:
+    for M, D in [(517, 3072), (3, 256), (64, 768), (5, 2048), (9, 4096), (1, 3072)]:
         x = torch.randn(M, D, device="cuda", generator=g).bfloat16()
         sc = (0.1 * torch.randn(D, device="cuda", generator=g)).bfloat16()
         sh = (0.1 * torch.randn(D, device="cuda", generator=g)).bfloat16()

@@ -28,14 +28,16 @@ def timeit(fn, reps):
         fn()
     tot = 0.0
     for _ in range(reps):
-        flush.zero_()                                            # evict L2 between timed launches
+        flush.max()                                              # evict L2 with a READ pass (clean lines: a memset
+                                                                 # would leave 126 MB of dirty lines to write back
+                                                                 # under the timed kernel)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); b.synchronize()
         tot += a.elapsed_time(b)
     return tot / reps
 
 
-print(f"# peak {peak} GB/s (MEASURED_PEAKS.json hbm_gbs); L2 flushed between launches")
+print(f"# peak {peak} GB/s (MEASURED_PEAKS.json hbm_gbs); L2 flushed (read pass over 256 MB) between launches")
 print("kernel rows bytes_per_launch us GB/s frac_of_peak")
 for rows in (4096, 4096 * args.images):
     ch = 64
