@@ -56,6 +56,10 @@ typedef struct rge_gemm_desc {
   const int32_t* rope_map; int32_t rope_off;                  /*   rope row = (rope_map?rope_map[m]:m)+rope_off */
 } rge_gemm_desc;
 int rge_op_gemm(const rge_gemm_desc* d, void* stream);
+/* n (1..6) independent GEMMs as ONE persistent launch: the q / k / v (/ MLP-up) projections of a block, or the image-
+ * and text-stream halves of one stage of a double block. Results are identical to n rge_op_gemm calls; members with
+ * M <= 0 are skipped. Members may read the same A and may write disjoint regions of the same buffers. */
+int rge_op_gemm_group(const rge_gemm_desc* descs, int32_t n, void* stream);
 
 /* O[Sq, H*128] = softmax(Q K^T * scale) V per head, non-causal, head_dim 128; replaces flash_attn_func
  * (inplace.py:796-801). K/V are the persistent cache [Skv, H*128]. */

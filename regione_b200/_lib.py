@@ -85,6 +85,7 @@ PROTOTYPES = {
     "rge_profile_collect": (c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(c_int64)]),
     "rge_op_gemm": (c_int32, [C.POINTER(GemmDesc), c_void_p]),
+    "rge_op_gemm_group": (c_int32, [C.POINTER(GemmDesc), c_int32, c_void_p]),
     "rge_op_attention": (c_int32, [C.POINTER(AttnDesc), c_void_p]),
     "rge_op_ln_modulate": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_void_p]),

@@ -167,6 +167,18 @@ int rge_op_gemm(const rge_gemm_desc* d, void* stream) {
   return RGE_OK;
 }
 
+int rge_op_gemm_group(const rge_gemm_desc* descs, int32_t n, void* stream) {
+  if (!descs || n < 1 || n > 6) return fail(RGE_ERR_INVALID, "rge_op_gemm_group: 1..6 descriptors expected");
+  GemmArgs a[6];
+  for (int i = 0; i < n; ++i) {
+    if (descs[i].M > 0 && (!descs[i].A || !descs[i].W || !descs[i].out))
+      return fail(RGE_ERR_INVALID, "rge_op_gemm_group: null operand in member %d", i);
+    a[i] = to_args(&descs[i]);
+  }
+  RGE_LAUNCH(launch_gemm_group(a, n, device_sms(), (cudaStream_t)stream));
+  return RGE_OK;
+}
+
 int rge_op_attention(const rge_attn_desc* d, void* stream) {
   if (!d || !d->Q || !d->K || !d->V || !d->O) return fail(RGE_ERR_INVALID, "rge_op_attention: null operand");
   AttnArgs a;
@@ -303,8 +315,8 @@ struct rge_handle {
   size_t pass_small_stride = 0;
   // independent GEMMs of one block run on library-owned side streams so that small-M launches (text stream,
   // region steps) fill the SMs the persistent grid of a neighbour leaves idle; joined before every attention
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_main = nullptr, ev_aux[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [3], [4]: text-stream K / V projections
+  cudaEvent_t ev_main = nullptr, ev_aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_txt = nullptr;
   bool fanout = true;
   // REGION steps: the attention grid (query-tile pairs x heads) rarely fills a whole number of waves of the SMs. In
   // the single-stream blocks the MLP-up GEMM is independent of attention, so attention runs on a high-priority stream
@@ -313,6 +325,9 @@ struct rge_handle {
   cudaStream_t sattn = nullptr;
   cudaEvent_t ev_attn = nullptr, ev_q = nullptr;
   bool fill_attn_tail = true;
+  // steps whose GEMMs all take the 1-CTA path (REGION steps: few rows) launch the independent GEMMs of a stage as one
+  // grouped persistent kernel instead of fanning them out over the side streams
+  bool grouped = true;
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
@@ -341,6 +356,28 @@ int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, 
   if (M <= 0) return RGE_OK;
   ProfScope prof(st, PC_GEMM, 2.0 * M * (double)N * K, M, N, K);
   RGE_LAUNCH(launch_gemm(a, sm_cap > 0 ? sm_cap : h->num_sms, st));
+  return RGE_OK;
+}
+
+GemmArgs mk(const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bias, int N, int epi, bf16* out, long ldo,
+            const int* row_map, int row_off, int col_off, const bf16* gate = nullptr, const bf16* res = nullptr,
+            long ldr = 0, const bf16* norm_w = nullptr, const float2* rope = nullptr, const int* rope_map = nullptr,
+            int rope_off = 0) {
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.M = M; a.K = K; a.W = W; a.ldw = K; a.N = N; a.bias = bias; a.epilogue = epi;
+  a.out = out; a.ldo = ldo; a.row_map = row_map; a.row_off = row_off; a.col_off = col_off;
+  a.gate = gate; a.res = res; a.ldr = ldr; a.norm_w = norm_w; a.rope_cs = rope; a.rope_map = rope_map;
+  a.rope_off = rope_off;
+  return a;
+}
+
+int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_cap = 0) {
+  double work = 0;
+  for (int i = 0; i < n; ++i)
+    if (a[i].M > 0) work += 2.0 * a[i].M * (double)a[i].N * a[i].K;
+  if (work == 0) return RGE_OK;
+  ProfScope prof(st, PC_GEMM, work, a[0].M, -n, a[0].K);   // N < 0 marks a group of |N| members in the timeline
+  RGE_LAUNCH(launch_gemm_group(a, n, sm_cap > 0 ? sm_cap : h->num_sms, st));
   return RGE_OK;
 }
 
@@ -398,10 +435,11 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   A(dalloc(&h->sel_img, S));
   A(dalloc(&h->sel_all, S));
   A(dalloc(&h->jobs, (size_t)2 + h->n_mod + 4 * cfg->n_pass));
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 5; ++i) {
     A(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&h->ev_aux[i], cudaEventDisableTiming));
   }
+  A(cudaEventCreateWithFlags(&h->ev_txt, cudaEventDisableTiming));
   A(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
   {
     int least = 0, greatest = 0;
@@ -412,6 +450,7 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   }
   if (const char* env = getenv("RGE_NO_FANOUT")) h->fanout = env[0] == '0' || env[0] == 0;
   if (const char* env = getenv("RGE_FILL_ATTN_TAIL")) h->fill_attn_tail = env[0] != '0';
+  if (const char* env = getenv("RGE_GROUPED")) h->grouped = env[0] != '0';
   if (e != cudaSuccess) {
     rge_destroy(h);
     return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));
@@ -430,10 +469,11 @@ int rge_destroy(rge_handle* h) {
                   h->rope, h->ids, h->sel_img, h->sel_all, h->jobs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 5; ++i) {
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
     if (h->ev_aux[i]) cudaEventDestroy(h->ev_aux[i]);
   }
+  if (h->ev_txt) cudaEventDestroy(h->ev_txt);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->sattn) cudaStreamDestroy(h->sattn);
   if (h->ev_attn) cudaEventDestroy(h->ev_attn);
@@ -614,6 +654,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   // K and V projections; `link(from, ev, to)` makes `to` wait for everything enqueued on `from` so far
   const bool fan = h->fanout;
   cudaStream_t sT = fan ? h->aux[0] : st, sK = fan ? h->aux[1] : st, sV = fan ? h->aux[2] : st;
+  cudaStream_t sTK = fan ? h->aux[3] : st, sTV = fan ? h->aux[4] : st;
   auto link = [&](cudaStream_t from, cudaEvent_t ev, cudaStream_t to) -> cudaError_t {
     if (from == to) return cudaSuccess;
     cudaError_t e = cudaEventRecord(ev, from);
@@ -634,97 +675,180 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   const int idle_sms = attn_tail ? h->num_sms - attn_tail : 0;
   const bool fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 &&
                          2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * 4.0 * 256.0 * S * 128.0;
-  // ---- double-stream blocks: image chain on `st`, text chain on sT, joined around attention
-  if (h->cfg.n_double > 0) RGE_CUDA(link(st, h->ev_main, sT));
-  for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
-    const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
-               *g_mlp = mod + 5 * D;
-    const bf16* cm = mod + 6 * D;
-    const bf16 *csh_msa = cm, *csc_msa = cm + D, *cg_msa = cm + 2 * D, *csh_mlp = cm + 3 * D, *csc_mlp = cm + 4 * D,
-               *cg_mlp = cm + 5 * D;
-    bf16* kc = h->kc(pass, layer);
-    bf16* vc = h->vc(pass, layer);
-    RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
-    RGE_CUDA(link(st, h->ev_main, sK));
-    RGE_CUDA(link(st, h->ev_main, sV));
-    // image stream q/k/v; k,v rows scattered into the cache at T + sel[m]
-    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr,
-                 T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T));
-    RGE_TRY(gemm(h, sK, n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D,
-                 h->sel_img, T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T));
-    RGE_TRY(gemm(h, sV, n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T,
-                 0));
-    // text stream q/k/v (recomputed every step: the reference does not cache text K/V)
-    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, sT));
-    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D,
-                 nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0));
-    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D,
-                 nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0));
-    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0,
-                 0));
-    RGE_CUDA(link(sT, h->ev_aux[0], st));
-    RGE_CUDA(link(sK, h->ev_aux[1], st));
-    RGE_CUDA(link(sV, h->ev_aux[2], st));
-    RGE_TRY(attention(kc, vc, st));
-    RGE_CUDA(link(st, h->ev_main, sT));
-    // out projections with gate * (.) + residual fused, then the feed-forward; each stream on its own chain
-    RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
-                 nullptr, 0, 0, g_msa, x_img, D));
-    RGE_TRY(gemm(h, sT, h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h,
-                 D, nullptr, 0, 0, cg_msa, h->h, D));
-    RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
-    RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, sT));
-    RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb,
-                 nullptr, 0, D));
-    RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb,
-                 nullptr, 0, D));
-    RGE_TRY(gemm(h, st, big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES,
-                 x_img, D, nullptr, 0, 0, g_mlp, x_img, D));
-    RGE_TRY(gemm(h, sT, h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES,
-                 h->h, D, nullptr, 0, 0, cg_mlp, h->h, D));
-  }
-  if (h->cfg.n_double > 0) RGE_CUDA(link(sT, h->ev_aux[0], st));
-  // ---- single-stream blocks on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
-  for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
-    const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
-    bf16* kc = h->kc(pass, layer);
-    bf16* vc = h->vc(pass, layer);
-    RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
-    if (!fill_tail) RGE_CUDA(link(st, h->ev_main, sT));
-    RGE_CUDA(link(st, h->ev_main, sK));
-    RGE_CUDA(link(st, h->ev_main, sV));
-    RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
-                 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0));
-    RGE_TRY(gemm(h, sK, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
-                 0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
-    RGE_TRY(gemm(h, sV, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
-                 0));
-    if (!fill_tail) {
-      RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
-                   nullptr, 0, D));
+  // A step whose widest GEMM (MA rows) stays below the CTA-pair kernel's threshold is a REGION step (or a small model):
+  // there every stage of a block is ONE grouped launch on `st` (no side streams, no events). FULL steps keep the
+  // fan-out below, where each large GEMM fills the GPU by itself.
+  const bool grouped = h->grouped && MA < 2048;
+  if (grouped) {
+    for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
+      const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
+                 *g_mlp = mod + 5 * D;
+      const bf16* cm = mod + 6 * D;
+      const bf16 *csh_msa = cm, *csc_msa = cm + D, *cg_msa = cm + 2 * D, *csh_mlp = cm + 3 * D, *csc_mlp = cm + 4 * D,
+                 *cg_mlp = cm + 5 * D;
+      bf16* kc = h->kc(pass, layer);
+      bf16* vc = h->vc(pass, layer);
+      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, st));
+      const GemmArgs qkv[6] = {
+          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, T, 0, nullptr,
+             nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T),
+          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_img, T, 0, nullptr,
+             nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T),
+          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T, 0),
+          mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0,
+             nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0),
+          mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D, nullptr, 0, 0,
+             nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0),
+          mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0, 0)};
+      RGE_TRY(gemm_group(h, st, qkv, 6));
+      RGE_TRY(attention(kc, vc, st));
+      const GemmArgs outp[2] = {
+          mk(big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D, nullptr, 0, 0,
+             g_msa, x_img, D),
+          mk(h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h, D, nullptr, 0,
+             0, cg_msa, h->h, D)};
+      RGE_TRY(gemm_group(h, st, outp, 2));
+      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, st));
+      const GemmArgs up[2] = {
+          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb, nullptr, 0, D),
+          mk(h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb, nullptr, 0, D)};
+      RGE_TRY(gemm_group(h, st, up, 2));
+      const GemmArgs down[2] = {
+          mk(big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES, x_img, D,
+             nullptr, 0, 0, g_mlp, x_img, D),
+          mk(h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES, h->h, D,
+             nullptr, 0, 0, cg_mlp, h->h, D)};
+      RGE_TRY(gemm_group(h, st, down, 2));
+    }
+    for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
+      const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
+      bf16* kc = h->kc(pass, layer);
+      bf16* vc = h->vc(pass, layer);
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
+      const GemmArgs proj[4] = {
+          mk(h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0, nullptr,
+             nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0),
+          mk(h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all, 0, 0, nullptr,
+             nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0),
+          mk(h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0, 0),
+          mk(h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr, 0, D)};
+      if (!fill_tail) {
+        RGE_TRY(gemm_group(h, st, proj, 4));
+        RGE_TRY(attention(kc, vc, st));
+      } else {
+        // attention (high priority) and the MLP GEMM (capped to the SMs its last wave leaves idle) start together
+        RGE_TRY(gemm_group(h, st, proj, 3));
+        RGE_CUDA(cudaEventRecord(h->ev_q, st));
+        RGE_CUDA(cudaStreamWaitEvent(h->sattn, h->ev_q, 0));
+        RGE_CUDA(cudaStreamWaitEvent(sT, h->ev_q, 0));
+        RGE_TRY(attention(kc, vc, h->sattn));
+        RGE_TRY(gemm_group(h, sT, proj + 3, 1, idle_sms));
+        RGE_CUDA(link(h->sattn, h->ev_attn, st));
+        RGE_CUDA(link(sT, h->ev_aux[0], st));
+      }
+      RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
+                   nullptr, 0, 0, g, h->h, D));
+    }
+  } else {
+    // ---- double-stream blocks: image chain on `st`, text chain on sT, joined around attention
+    if (h->cfg.n_double > 0) RGE_CUDA(link(st, h->ev_main, sT));
+    for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
+      const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
+                 *g_mlp = mod + 5 * D;
+      const bf16* cm = mod + 6 * D;
+      const bf16 *csh_msa = cm, *csc_msa = cm + D, *cg_msa = cm + 2 * D, *csh_mlp = cm + 3 * D, *csc_mlp = cm + 4 * D,
+                 *cg_mlp = cm + 5 * D;
+      bf16* kc = h->kc(pass, layer);
+      bf16* vc = h->vc(pass, layer);
+      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
+      RGE_CUDA(link(st, h->ev_main, sK));
+      RGE_CUDA(link(st, h->ev_main, sV));
+      // image stream q/k/v; k,v rows scattered into the cache at T + sel[m]
+      RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr,
+                   T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T));
+      RGE_TRY(gemm(h, sK, n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D,
+                   h->sel_img, T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T));
+      RGE_TRY(gemm(h, sV, n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T,
+                   0));
+      // text stream q/k/v (recomputed every step: the reference does not cache text K/V)
+      // the three text projections are small (T rows): on one stream they would run back to back on a mostly idle GPU
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, sT));
+      RGE_CUDA(link(sT, h->ev_txt, sTK));
+      RGE_CUDA(link(sT, h->ev_txt, sTV));
+      RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D,
+                   nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0));
+      RGE_TRY(gemm(h, sTK, h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D,
+                   nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0));
+      RGE_TRY(gemm(h, sTV, h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr,
+                   0, 0));
+      RGE_CUDA(link(sT, h->ev_aux[0], st));
       RGE_CUDA(link(sK, h->ev_aux[1], st));
       RGE_CUDA(link(sV, h->ev_aux[2], st));
+      RGE_CUDA(link(sTK, h->ev_aux[3], st));
+      RGE_CUDA(link(sTV, h->ev_aux[4], st));
       RGE_TRY(attention(kc, vc, st));
-      // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT: its CTAs and
-      // the attention CTAs share the SMs, which fills the partial last wave of either kernel
-    } else {
-      // attention (high priority) and the MLP GEMM (capped to the idle SMs) both start once q, k and v are done
-      RGE_CUDA(cudaEventRecord(h->ev_q, st));
-      RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
-      RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
-      for (cudaStream_t s2 : {h->sattn, sT}) {
-        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_q, 0));
-        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[1], 0));
-        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[2], 0));
-      }
-      RGE_TRY(attention(kc, vc, h->sattn));
-      RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
-                   nullptr, 0, D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, idle_sms));
-      RGE_CUDA(link(h->sattn, h->ev_attn, st));
+      RGE_CUDA(link(st, h->ev_main, sT));
+      // out projections with gate * (.) + residual fused, then the feed-forward; each stream on its own chain
+      RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
+                   nullptr, 0, 0, g_msa, x_img, D));
+      RGE_TRY(gemm(h, sT, h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h,
+                   D, nullptr, 0, 0, cg_msa, h->h, D));
+      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, sT));
+      RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb,
+                   nullptr, 0, D));
+      RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb,
+                   nullptr, 0, D));
+      RGE_TRY(gemm(h, st, big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES,
+                   x_img, D, nullptr, 0, 0, g_mlp, x_img, D));
+      RGE_TRY(gemm(h, sT, h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES,
+                   h->h, D, nullptr, 0, 0, cg_mlp, h->h, D));
     }
-    RGE_CUDA(link(sT, h->ev_aux[0], st));
-    RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
-                 nullptr, 0, 0, g, h->h, D));
+    if (h->cfg.n_double > 0) RGE_CUDA(link(sT, h->ev_aux[0], st));
+    // ---- single-stream blocks on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
+    for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
+      const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
+      bf16* kc = h->kc(pass, layer);
+      bf16* vc = h->vc(pass, layer);
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
+      if (!fill_tail) RGE_CUDA(link(st, h->ev_main, sT));
+      RGE_CUDA(link(st, h->ev_main, sK));
+      RGE_CUDA(link(st, h->ev_main, sV));
+      RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
+                   0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0));
+      RGE_TRY(gemm(h, sK, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
+                   0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
+      RGE_TRY(gemm(h, sV, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
+                   0));
+      if (!fill_tail) {
+        RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
+                     nullptr, 0, D));
+        RGE_CUDA(link(sK, h->ev_aux[1], st));
+        RGE_CUDA(link(sV, h->ev_aux[2], st));
+        RGE_TRY(attention(kc, vc, st));
+        // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT: its CTAs and
+        // the attention CTAs share the SMs, which fills the partial last wave of either kernel
+      } else {
+        // attention (high priority) and the MLP GEMM (capped to the idle SMs) both start once q, k and v are done
+        RGE_CUDA(cudaEventRecord(h->ev_q, st));
+        RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
+        RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
+        for (cudaStream_t s2 : {h->sattn, sT}) {
+          RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_q, 0));
+          RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[1], 0));
+          RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[2], 0));
+        }
+        RGE_TRY(attention(kc, vc, h->sattn));
+        RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
+                     nullptr, 0, D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, idle_sms));
+        RGE_CUDA(link(h->sattn, h->ev_attn, st));
+      }
+      RGE_CUDA(link(sT, h->ev_aux[0], st));
+      RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
+                   nullptr, 0, 0, g, h->h, D));
+    }
   }
   // ---- norm_out (scale first, then shift) + proj_out on the noise rows only (App. C-9)
   RGE_LAUNCH(launch_ln_modulate(x_img, D, mod, mod + D, n_img_p, D, n_out, D, st));

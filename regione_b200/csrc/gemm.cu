@@ -158,6 +158,161 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------- grouped launch
+// Up to kMaxGroup independent GEMMs (own operands, shapes, tile widths and epilogues) as ONE persistent launch whose
+// tile list is the concatenation of the members' tiles. The q / k / v (/ MLP-up) projections of a block, or the
+// image- and text-stream halves of one stage of a double block, are such groups: launched one by one each of them
+// fills a fraction of a wave of the 148 SMs and pays its own prologue; grouped, the CTAs stream through all tiles.
+constexpr int kMaxGroup = 6;
+
+struct GroupParams {
+  CUtensorMap map_a[kMaxGroup];
+  CUtensorMap map_b[kMaxGroup];
+  GemmDev p[kMaxGroup];
+  int tile_end[kMaxGroup];   // running end of each member's tile range (members sorted by decreasing tile cost)
+  int num_m[kMaxGroup];
+  int bn[kMaxGroup];
+  int epi[kMaxGroup];
+  int n_prob;
+  int stages;
+  int stage_bytes;           // kABytes + widest member's B tile
+};
+
+struct GroupTile { int prob, m_blk, n_blk; };
+
+__device__ __forceinline__ GroupTile group_decode(const GroupParams& g, int tile) {
+  GroupTile t;
+  t.prob = 0;
+  int start = 0;
+  while (tile >= g.tile_end[t.prob]) { start = g.tile_end[t.prob]; ++t.prob; }
+  const int local = tile - start;
+  t.m_blk = local % g.num_m[t.prob];
+  t.n_blk = local / g.num_m[t.prob];
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_group_kernel(const __grid_constant__ GroupParams g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_stages = g.stages;
+  const int stage_bytes = g.stage_bytes;
+  const int num_tiles = g.tile_end[g.n_prob - 1];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.n_prob; ++i) {
+      tma_prefetch_desc(&g.map_a[i]);
+      tma_prefetch_desc(&g.map_b[i]);
+    }
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const GroupTile t = group_decode(g, tile);
+        const int bn = g.bn[t.prob];
+        const int num_kb = (g.p[t.prob].K + BK - 1) / BK;
+        const uint32_t bytes = kABytes + bn * BK * 2;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          tma_load_2d(sa, &g.map_a[t.prob], &full_bar[stage], kb * BK, t.m_blk * BM);
+          tma_load_2d(sb, &g.map_b[t.prob], &full_bar[stage], kb * BK, t.n_blk * bn);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const GroupTile t = group_decode(g, tile);
+        const uint32_t idesc = make_idesc_bf16(BM, g.bn[t.prob], 0, 0);
+        const int num_kb = (g.p[t.prob].K + BK - 1) / BK;
+        const int acc = it & 1;
+        const uint32_t use = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], use ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t a_desc = make_sdesc_sw128(sa, 0, 1024);
+          const uint64_t b_desc = make_sdesc_sw128(sb, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[stage]);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const GroupTile t = group_decode(g, tile);
+      const int bn = g.bn[t.prob];
+      const int acc = it & 1;
+      const uint32_t use = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], use);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * kMaxBN;
+      const GemmDev& p = g.p[t.prob];
+      const int m = t.m_blk * BM + r, n0 = t.n_blk * bn;
+      switch (g.epi[t.prob]) {
+        case EPI_STORE: gemm_epilogue_row<EPI_STORE>(p, taddr, m, n0, bn); break;
+        case EPI_GELU: gemm_epilogue_row<EPI_GELU>(p, taddr, m, n0, bn); break;
+        case EPI_GATE_RES: gemm_epilogue_row<EPI_GATE_RES>(p, taddr, m, n0, bn); break;
+        default: gemm_epilogue_row<EPI_NORM_ROPE>(p, taddr, m, n0, bn); break;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // Tile width for the 1-CTA kernel: minimise  waves x (bn + fixed per-tile cost)  over the widths the epilogue allows.
 // The fixed cost (in output columns) stands for the prologue / epilogue drain of a tile and for the A-tile re-reads of
 // narrow tiles; ties go to the wider tile. RGE_GEMM_BN=<n> forces a width (tuning / tests).
@@ -218,7 +373,88 @@ cudaError_t launch_1cta(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
+bool gemm_args_ok(const GemmArgs& a) {
+  if (a.K <= 0 || (a.K % 8) || (a.N % 32) || (a.lda % 8) || (a.ldw % 8) || (a.ldo % 8) || (a.col_off % 8)) return false;
+  if (a.epilogue < EPI_STORE || a.epilogue > EPI_NORM_ROPE) return false;
+  if (a.epilogue == EPI_NORM_ROPE && ((a.N % 128) || !a.norm_w || !a.rope_cs)) return false;
+  if (a.epilogue == EPI_GATE_RES && (!a.gate || !a.res || (a.ldr % 8))) return false;
+  return a.A && a.W && a.out;
+}
+
 }  // namespace
+
+cudaError_t launch_gemm_group(const GemmArgs* args, int n, int num_sms, cudaStream_t stream) {
+  const GemmArgs* live[kMaxGroup];
+  int n_live = 0;
+  for (int i = 0; i < n; ++i) {
+    if (args[i].M <= 0 || args[i].N <= 0) continue;   // empty member (e.g. no edited token): nothing to do
+    if (!gemm_args_ok(args[i]) || n_live == kMaxGroup) return cudaErrorInvalidValue;
+    live[n_live++] = &args[i];
+  }
+  if (n_live == 0) return cudaSuccess;
+  if (n_live == 1) return launch_gemm(*live[0], num_sms, stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // one width cap for the whole group: every member takes its widest allowed tile <= cap; the cap minimises
+  //   (sum of tile costs) / SMs  +  half the longest tile   with tile cost = (bn + 32) * K
+  // (the 32 stands for per-tile overhead and A re-reads of narrow tiles, the second term for the ragged last wave)
+  const int caps[] = {256, 224, 192, 160, 128, 96, 64};
+  auto width = [](const GemmArgs& a, int cap) {
+    if (a.epilogue == EPI_NORM_ROPE) return cap >= 256 ? 256 : 128;
+    return cap;
+  };
+  int best_cap = 256;
+  double best_cost = 0;
+  for (int c = 0; c < 7; ++c) {
+    double sum = 0, longest = 0;
+    for (int i = 0; i < n_live; ++i) {
+      const GemmArgs& a = *live[i];
+      const int bn = width(a, caps[c]);
+      const double tile_cost = (double)(bn + 32) * a.K;
+      sum += tile_cost * ((a.M + BM - 1) / BM) * ((a.N + bn - 1) / bn);
+      if (tile_cost > longest) longest = tile_cost;
+    }
+    const double cost = sum / num_sms + 0.5 * longest;
+    if (c == 0 || cost < best_cost) { best_cap = caps[c]; best_cost = cost; }
+  }
+  // longest tiles first, so that the short ones even out the end of the launch
+  int order[kMaxGroup];
+  for (int i = 0; i < n_live; ++i) order[i] = i;
+  for (int i = 1; i < n_live; ++i)
+    for (int j = i; j > 0; --j) {
+      const GemmArgs &x = *live[order[j]], &y = *live[order[j - 1]];
+      if ((double)(width(x, best_cap) + 32) * x.K > (double)(width(y, best_cap) + 32) * y.K) {
+        const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+      } else break;
+    }
+  GroupParams g;
+  int max_bn = 0, tiles = 0;
+  for (int k = 0; k < n_live; ++k) {
+    const GemmArgs& a = *live[order[k]];
+    const int bn = width(a, best_cap);
+    if (!make_tmap_bf16_2d(&g.map_a[k], a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16_2d(&g.map_b[k], a.W, a.N, a.K, a.ldw, bn)) return cudaErrorInvalidValue;
+    g.p[k] = to_dev(a);
+    g.num_m[k] = (a.M + BM - 1) / BM;
+    g.bn[k] = bn;
+    g.epi[k] = a.epilogue;
+    tiles += g.num_m[k] * ((a.N + bn - 1) / bn);
+    g.tile_end[k] = tiles;
+    if (bn > max_bn) max_bn = bn;
+  }
+  for (int k = n_live; k < kMaxGroup; ++k) g.tile_end[k] = tiles;
+  g.n_prob = n_live;
+  g.stage_bytes = kABytes + max_bn * BK * 2;
+  g.stages = kRingBytes / g.stage_bytes;
+  if (g.stages > kMaxStages) g.stages = kMaxStages;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_group_kernel<<<grid, kThreads, kSmemBytes, stream>>>(g);
+  return cudaGetLastError();
+}
 
 void* get_tensor_map_encoder() { return reinterpret_cast<void*>(tensor_map_encoder()); }
 

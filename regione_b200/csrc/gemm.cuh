@@ -41,6 +41,9 @@ struct GemmArgs {
 // Launches on `stream`; returns cudaSuccess or the launch/encode error. `num_sms` bounds the persistent grid.
 cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 
+// Up to 6 independent GEMMs (1-CTA tiles) as one persistent launch; members with M <= 0 are skipped.
+cudaError_t launch_gemm_group(const GemmArgs* args, int n, int num_sms, cudaStream_t stream);
+
 // Resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency).
 void* get_tensor_map_encoder();
 

@@ -18,17 +18,14 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise _lib.RegionEB200Error(f"{name}: innermost dimension must be contiguous")
 
 
-def gemm(a, w, bias=None, *, epilogue=_lib.EPI_STORE, out=None, row_map=None, row_off=0, col_off=0, gate=None,
-         res=None, norm_w=None, rope_cs=None, rope_map=None, rope_off=0):
-    """out[(row_map[m] or m)+row_off, col_off+n] = epilogue(a[M,K] @ w[N,K]^T + bias)."""
-    lib = _lib.load()
+def _gemm_desc(d, a, w, bias=None, *, epilogue=_lib.EPI_STORE, out=None, row_map=None, row_off=0, col_off=0, gate=None,
+               res=None, norm_w=None, rope_cs=None, rope_map=None, rope_off=0):
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
     M, K = a.shape
     N = w.shape[0]
     if out is None:
         out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
     _req(out, torch.bfloat16, "out")
-    d = GemmDesc()
     d.A, d.lda = ptr(a), a.stride(0)
     d.W, d.ldw = ptr(w), w.stride(0)
     d.bias = ptr(bias)
@@ -39,8 +36,25 @@ def gemm(a, w, bias=None, *, epilogue=_lib.EPI_STORE, out=None, row_map=None, ro
     d.gate, d.res, d.ldr = ptr(gate), ptr(res), (res.stride(0) if res is not None else 0)
     d.norm_w, d.rope_cs = ptr(norm_w), ptr(rope_cs)
     d.rope_map, d.rope_off = ptr(rope_map), rope_off
+    return out
+
+
+def gemm(a, w, bias=None, **kw):
+    """out[(row_map[m] or m)+row_off, col_off+n] = epilogue(a[M,K] @ w[N,K]^T + bias)."""
+    lib = _lib.load()
+    d = GemmDesc()
+    out = _gemm_desc(d, a, w, bias, **kw)
     check(lib.rge_op_gemm(C.byref(d), stream_ptr()), "rge_op_gemm")
     return out
+
+
+def gemm_group(members):
+    """`members`: list of (a, w, bias, kwargs-of-gemm) run as ONE persistent launch; returns the list of outputs."""
+    lib = _lib.load()
+    descs = (GemmDesc * len(members))()
+    outs = [_gemm_desc(descs[i], a, w, bias, **kw) for i, (a, w, bias, kw) in enumerate(members)]
+    check(lib.rge_op_gemm_group(descs, len(members), stream_ptr()), "rge_op_gemm_group")
+    return outs
 
 
 def attention(q, k, v, heads: int, out=None, scale: float | None = None):

@@ -323,3 +323,65 @@ def test_pack_unpack_latents_bit_exact(B, C, H, W):
     assert torch.equal(back, ref_back) and torch.equal(back, x)
     from regione_b200.standin import FluxKontextPipeline
     assert torch.equal(FluxKontextPipeline._unpack_latents(FluxKontextPipeline._pack_latents(x), H * 8, W * 8, 8), x)
+
+
+def test_gemm_group_equals_single_launches():
+    """rge_op_gemm_group: the q / k / v (/ MLP-up) projections of a block as one persistent launch. Same tiles, same
+    K order -> bit-identical to the members launched one by one; mixed epilogues, shapes, K, scatter, an empty member."""
+    from regione_b200 import _lib, ops
+    g = _gen(51)
+    D, Dm, S, T, M = 512, 1024, 2600, 200, 1064
+
+    def lin(n, k):
+        return ((torch.randn(n, k, device="cuda", generator=g) * 0.05).bfloat16(),
+                torch.randn(n, device="cuda", generator=g).bfloat16())
+
+    x_img = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    x_txt = torch.randn(T, D, device="cuda", generator=g).bfloat16()
+    sel = (torch.randperm(S - T, device="cuda", generator=g)[:M].sort().values + T).int()
+    nw = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
+    ids = torch.zeros(S, 3, device="cuda")
+    ids[:, 1] = torch.arange(S, device="cuda") // 50
+    ids[:, 2] = torch.arange(S, device="cuda") % 50
+    cs = ops.rope_table(ids)
+    (wq, bq), (wk, bk), (wv, bv), (wm, bm) = lin(D, D), lin(D, D), lin(D, D), lin(Dm, D)
+    (wtq, btq), (wdown, bdown) = lin(D, D), lin(D, Dm)
+    gate = torch.randn(D, device="cuda", generator=g).bfloat16()
+    hid = torch.randn(M, Dm, device="cuda", generator=g).bfloat16()
+    res0 = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    empty = torch.empty(0, D, device="cuda", dtype=torch.bfloat16)
+
+    def members(q, kc, vc, big, res, qe):
+        return [
+            (x_img, wq, bq, dict(epilogue=_lib.EPI_NORM_ROPE, out=q, row_off=T, norm_w=nw, rope_cs=cs, rope_map=sel)),
+            (x_img, wk, bk, dict(epilogue=_lib.EPI_NORM_ROPE, out=kc, row_map=sel, norm_w=nw, rope_cs=cs, rope_map=sel)),
+            (x_img, wv, bv, dict(out=vc, row_map=sel)),
+            (x_txt, wtq, btq, dict(epilogue=_lib.EPI_NORM_ROPE, out=q, norm_w=nw, rope_cs=cs)),
+            (x_img, wm, bm, dict(epilogue=_lib.EPI_GELU, out=big, col_off=D)),
+            (hid, wdown, bdown, dict(epilogue=_lib.EPI_GATE_RES, out=res, gate=gate, res=res)),
+        ], (empty, wq, bq, dict(out=qe))
+
+    def buffers():
+        return (torch.zeros(T + M, D, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(S, D, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(S, D, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(M, D + Dm, device="cuda", dtype=torch.bfloat16), res0.clone(),
+                torch.empty(0, D, device="cuda", dtype=torch.bfloat16))
+
+    ref = buffers()
+    mem, emp = members(*ref)
+    for a, w, b, kw in mem:
+        ops.gemm(a, w, b, **kw)
+    got = buffers()
+    mem, emp = members(*got)
+    ops.gemm_group(mem[:3] + [emp] + [mem[3]])          # 5 descriptors, one of them empty
+    ops.gemm_group([mem[4], mem[5]])                    # different K (512 / 1024) and tile widths in one launch
+    one = torch.zeros(S, D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_group([(x_img, wv, bv, dict(out=one, row_map=sel))])   # a group of one falls through to the plain launch
+    assert torch.equal(one, ref[2])
+    torch.cuda.synchronize()
+    for r, o in zip(ref[:5], got[:5]):
+        assert torch.equal(r, o)
+    assert rel_l2(got[2][sel.long()], F.linear(x_img, wv, bv)) <= BF16_TOL
+    assert rel_l2(got[3][:, D:], F.gelu(F.linear(x_img, wm, bm), approximate="tanh")) <= BF16_TOL
+    assert rel_l2(got[4], res0 + gate[None] * F.linear(hid, wdown, bdown)) <= BF16_TOL
