@@ -325,9 +325,12 @@ struct rge_handle {
   cudaStream_t sattn = nullptr;
   cudaEvent_t ev_attn = nullptr, ev_q = nullptr;
   bool fill_attn_tail = true;
-  // steps whose GEMMs all take the 1-CTA path (REGION steps: few rows) launch the independent GEMMs of a stage as one
-  // grouped persistent kernel instead of fanning them out over the side streams
-  bool grouped = true;
+  // RGE_GROUPED=1: steps whose GEMMs all take the 1-CTA path (REGION steps: few rows) launch the independent GEMMs of
+  // a stage as ONE grouped persistent kernel on the caller's stream instead of fanning them out over the side
+  // streams. Off by default: measured 43.5 ms vs 41.5 ms per REGION step (profiles/r01_step_times_grouped*.log) -
+  // the pre-attention stage gets faster (119 vs 184 us) but the free-running image / text chains after attention,
+  // which overlap with the next block in the fan-out, are serialised at every stage.
+  bool grouped = false;
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
