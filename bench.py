@@ -32,6 +32,16 @@ GRID, TXT = 64, 512            # 1024x1024 -> 64x64 latent tokens; max_sequence_
 FULL_STEPS = 9
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant GEMM shape, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by hand from profiles/rNN_prof_gemm2_summary.csv).
+    None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -247,7 +257,9 @@ def run_ours(args):
         "roofline": {
             "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all epilogues)", "bound": "tensor",
             "achieved": round(gemm_tf, 1) if gemm_tf else None, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": round(gemm_tf / peaks["tf_sustained"], 4) if gemm_tf else None, "traffic": None,
+            "frac": round(gemm_tf / peaks["tf_sustained"], 4) if gemm_tf else None,
+            "traffic": (load_traffic() or {}).get("dram_bytes_per_launch"),
+            "traffic_note": (load_traffic() or {}).get("note", "no ncu --set full capture committed"),
             "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
             "launches": int(pcnt[0]), "avg_launch_ms": round(psum[0] / max(pcnt[0], 1), 4),
             "share_of_step": round(pms[0] / ms, 4),
