@@ -196,44 +196,70 @@ __global__ void __launch_bounds__(256, 4) ln_modulate_wide_kernel(const __nv_bfl
     unpack8(__ldg(sc + t + 128 * i), a);
     unpack8(__ldg(sh + t + 128 * i), b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float n = bf16_round((f[j] - mean) * rstd);
-      const float tt = bf16_round(n * bf16_round(1.0f + a[j]));
-      f[j] = tt + b[j];
+    for (int j = 0; j < 8; j += 2) {   // the reference's bf16 rounding points, two elements per packed conversion
+      float n0 = (f[j] - mean) * rstd, n1 = (f[j + 1] - mean) * rstd;
+      bf16_round2(n0, n1);
+      float s0 = 1.0f + a[j], s1 = 1.0f + a[j + 1];
+      bf16_round2(s0, s1);
+      float t0 = n0 * s0, t1 = n1 * s1;
+      bf16_round2(t0, t1);
+      f[j] = t0 + b[j];
+      f[j + 1] = t1 + b[j + 1];
     }
     o[t + 128 * i] = pack8(f);
   }
 }
 
 // ------------------------------------------------------------------ batched GEMV
+// One block = 32 consecutive output rows of one job (8 warps x 4 rows): the input vector (with its optional SiLU) is
+// staged once per block in shared memory and every lane keeps four independent 128-bit weight loads in flight. The
+// per-row accumulation order (lane-strided, then a warp shuffle tree) does not depend on the rows-per-warp factor.
+constexpr int kGemvRowsPerWarp = 4;
+constexpr int kGemvRowsPerBlock = 8 * kGemvRowsPerWarp;
+
 __global__ void __launch_bounds__(256) gemv_batch_kernel(const GemvJob* __restrict__ jobs) {
   extern __shared__ float xs[];
   const GemvJob job = jobs[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x * 8 >= job.N) return;
+  if (blockIdx.x * kGemvRowsPerBlock >= job.N) return;
   for (int k = threadIdx.x; k < job.K; k += blockDim.x) {
     float v = __bfloat162float(job.x[k]);
     if (job.silu_in) v = bf16_round(silu_f(v));
     xs[k] = v;
   }
   __syncthreads();
-  const int n = blockIdx.x * 8 + warp;
-  if (n >= job.N) return;
-  const uint4* wr = reinterpret_cast<const uint4*>(job.W + (long)n * job.K);
+  const int n0 = blockIdx.x * kGemvRowsPerBlock + warp * kGemvRowsPerWarp;
+  if (n0 >= job.N) return;
   const int nv = job.K >> 3;
-  float acc = 0.f;
+  const uint4* wr[kGemvRowsPerWarp];
+  float acc[kGemvRowsPerWarp];
+#pragma unroll
+  for (int r = 0; r < kGemvRowsPerWarp; ++r) {
+    wr[r] = reinterpret_cast<const uint4*>(job.W + (long)min(n0 + r, job.N - 1) * job.K);
+    acc[r] = 0.f;
+  }
   for (int i = lane; i < nv; i += 32) {
-    float f[8];
-    unpack8(__ldg(wr + i), f);
+    uint4 w[kGemvRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kGemvRowsPerWarp; ++r) w[r] = __ldg(wr[r] + i);
     const float* xv = xs + i * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(f[j], xv[j], acc);
+    for (int r = 0; r < kGemvRowsPerWarp; ++r) {
+      float f[8];
+      unpack8(w[r], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[r] = fmaf(f[j], xv[j], acc[r]);
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    float y = bf16_round(acc + (job.b ? __bfloat162float(job.b[n]) : 0.f));
-    if (job.silu_out) y = silu_f(y);
-    job.out[n] = __float2bfloat16_rn(y);
+#pragma unroll
+  for (int r = 0; r < kGemvRowsPerWarp; ++r) {
+    const float a = warp_sum(acc[r]);
+    const int n = n0 + r;
+    if (lane == 0 && n < job.N) {
+      float y = bf16_round(a + (job.b ? __bfloat162float(job.b[n]) : 0.f));
+      if (job.silu_out) y = silu_f(y);
+      job.out[n] = __float2bfloat16_rn(y);
+    }
   }
 }
 
@@ -636,7 +662,7 @@ cudaError_t launch_cfg_combine(const __nv_bfloat16* pos, const __nv_bfloat16* ne
 
 cudaError_t launch_gemv_batch(const GemvJob* jobs_dev, int n_jobs, int max_n, cudaStream_t s) {
   if (n_jobs <= 0) return cudaSuccess;
-  dim3 grid(cdiv(max_n, 8), n_jobs);
+  dim3 grid(cdiv(max_n, kGemvRowsPerBlock), n_jobs);
   gemv_batch_kernel<<<grid, 256, 4096 * sizeof(float), s>>>(jobs_dev);  // K <= 4096 (checked by the caller)
   return cudaGetLastError();
 }

@@ -91,7 +91,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
@@ -140,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int r = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
       const int acc = it & 1;
       const uint32_t use = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], use);
@@ -356,7 +356,8 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   CUtensorMap map_a, map_b;
   if (!make_tmap_bf16_2d(&map_a, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, cfg.bn)) return cudaErrorInvalidValue;
-  const GemmDev p = to_dev(a);
+  GemmDev p = to_dev(a);
+  p.n_fast = pick_n_fast(a);
   const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + cfg.bn - 1) / cfg.bn);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, cfg);

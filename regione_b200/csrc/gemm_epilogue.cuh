@@ -1,6 +1,7 @@
 // Fused GEMM epilogues shared by the 1-CTA (gemm.cu) and 2-CTA (gemm2.cu) tcgen05 kernels: one thread owns one
 // output row of the accumulator tile in TMEM and walks its columns in chunks of 32.
 #pragma once
+#include <cstdlib>
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -20,7 +21,25 @@ struct GemmDev {
   const float2* rope_cs;
   const int* rope_map;
   int rope_off;
+  int n_fast;   // tile order: 0 = consecutive tiles walk down M (W tile shared, A streamed), 1 = walk along N
 };
+
+// Tile order. A wave of concurrent tiles re-streams one operand from L2 / DRAM for every few blocks of the other
+// dimension. Walking down M keeps the current W tiles hot and streams A once per ~2 column blocks, which is free while
+// A (M x K) fits in the 126 MB L2 (K = 3072: 53 MB) and costs 4-5x the algorithmic DRAM reads when it does not
+// (FF-down, K = 12288: 201 MB; single-block proj_out, K = 15360: 267 MB; ncu: 1.28 GB read per launch instead of
+// 0.33 GB). Those launches walk along N instead: A is read once band by band and W (75 - 94 MB) is the operand that
+// lives in L2. RGE_RASTER=m|n forces one order (tuning).
+inline int pick_n_fast(const GemmArgs& a) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* env = getenv("RGE_RASTER");
+    forced = !env ? -1 : (env[0] == 'n' ? 1 : (env[0] == 'm' ? 0 : -1));
+  }
+  if (forced >= 0) return forced;
+  const double a_bytes = 2.0 * a.M * a.K, w_bytes = 2.0 * a.N * a.K;
+  return a_bytes > 96e6 && w_bytes < a_bytes ? 1 : 0;
+}
 
 inline GemmDev to_dev(const GemmArgs& a) {
   GemmDev p;
@@ -28,6 +47,7 @@ inline GemmDev to_dev(const GemmArgs& a) {
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.row_map = a.row_map; p.row_off = a.row_off; p.col_off = a.col_off;
   p.gate = a.gate; p.res = a.res; p.ldr = a.ldr;
   p.norm_w = a.norm_w; p.rope_cs = a.rope_cs; p.rope_map = a.rope_map; p.rope_off = a.rope_off;
+  p.n_fast = 0;
   return p;
 }
 

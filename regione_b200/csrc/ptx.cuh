@@ -278,6 +278,13 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, u
 
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Two roundings with one packed conversion (cvt.rn.bf16x2.f32) and two bit operations.
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  const uint32_t u = *reinterpret_cast<uint32_t*>(&t);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&t);

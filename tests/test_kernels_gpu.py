@@ -39,7 +39,8 @@ def test_gemm_store_matches_linear(M, N, K):
     assert rel_l2(y2, a.float() @ w.float().t()) <= BF16_TOL
 
 
-@pytest.mark.parametrize("M,N,K", [(2048, 256, 64), (2049, 512, 192), (4000, 3072, 256), (2304, 768, 3072)])
+@pytest.mark.parametrize("M,N,K", [(2048, 256, 64), (2049, 512, 192), (4000, 3072, 256), (2304, 768, 3072),
+                                   (4100, 512, 12288)])   # last: A > 96 MB -> tiles walk along N (pick_n_fast)
 def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
     """M >= 2048 and N % 256 == 0 dispatch to the cta_group::2 kernel (gemm2.cu): ragged M (second CTA partly or
     fully out of range), every epilogue, scatter."""
