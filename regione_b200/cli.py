@@ -74,7 +74,9 @@ def build_parser(family: str) -> argparse.ArgumentParser:
     # synthetic source only
     p.add_argument("--grid", type=int, nargs=2, default=None, help="synthetic: latent token grid (rows cols)")
     p.add_argument("--txt_len", type=int, default=None, help="synthetic: prompt tokens")
-    p.add_argument("--rho", type=float, default=0.25, help="synthetic: edited fraction of each image")
+    p.add_argument("--rho", type=str, default="0.25",
+                   help="synthetic: edited fraction of each image, or `sweep` = per item one of 5/10/15/25/40/60/100 %% "
+                        "(SURVEY §8d config 5)")
     p.add_argument("--no_warmup", action="store_true", help="skip the 3 warm-up images")
     return p
 
@@ -90,6 +92,20 @@ def _load_real(family: str, args):
     cls = getattr(diffusers, FAMILIES[family][0])
     pipe = cls.from_pretrained(args.model_path, torch_dtype=torch.bfloat16).to(args.device)
     return pipe
+
+
+RHO_SWEEP = (0.05, 0.10, 0.15, 0.25, 0.40, 0.60, 1.00)
+
+
+def _rho(args, seed: int) -> float:
+    return RHO_SWEEP[seed % len(RHO_SWEEP)] if args.rho == "sweep" else float(args.rho)
+
+
+def _shard(items):
+    """Data-parallel runs (one process per GPU under torchrun; script/*.sh of the reference are run once per GPU on a
+    slice of the benchmark): rank r of W takes items r, r + W, ... No collective is involved."""
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    return items[rank::world] if world > 1 else items
 
 
 def _synthetic(family: str, args):
@@ -117,7 +133,7 @@ def _synthetic(family: str, args):
         ctx, pooled = arch["ctx_dim"], arch["pooled_dim"]
 
         def inputs(seed):
-            i = syn.make_inputs(seed, gh, gw, T, ctx, pooled, rho=args.rho, device=dev)
+            i = syn.make_inputs(seed, gh, gw, T, ctx, pooled, rho=_rho(args, seed), device=dev)
             i.pop("intended_mask")
             return i
     elif family in ("Step1X-Edit", "Step1X-Edit-v1p2"):
@@ -132,7 +148,7 @@ def _synthetic(family: str, args):
         ctx = tr.context_embedder.in_features
 
         def inputs(seed):
-            i = syn.make_inputs(seed, gh, gw, T, ctx, 64, rho=args.rho, device=dev)
+            i = syn.make_inputs(seed, gh, gw, T, ctx, 64, rho=_rho(args, seed), device=dev)
             g = torch.Generator().manual_seed(seed + 1)
             neg = (0.1 * torch.randn(1, T, ctx, generator=g)).to(dev, torch.bfloat16)
             mask = torch.ones(1, T, dtype=torch.long, device=dev)
@@ -158,7 +174,7 @@ def _synthetic(family: str, args):
         ctx = arch["ctx_dim"]
 
         def inputs(seed):
-            i = syn.make_inputs(seed, gh, gw, T, ctx, 64, rho=args.rho, device=dev)
+            i = syn.make_inputs(seed, gh, gw, T, ctx, 64, rho=_rho(args, seed), device=dev)
             g = torch.Generator().manual_seed(seed + 1)
             neg = (0.1 * torch.randn(1, T, ctx, generator=g)).to(dev, torch.bfloat16)
             return dict(latents=i["latents"], image_latents=i["image_latents"], prompt_embeds=i["prompt_embeds"],
@@ -181,6 +197,9 @@ def main(argv=None) -> int:
     args = build_parser(family).parse_args(argv)
     if not torch.cuda.is_available() or not str(args.device).startswith("cuda"):
         raise SystemExit("regione_b200.cli: the hot path is CUDA-only (sm_100a); there is no CPU fallback")
+    if "LOCAL_RANK" in os.environ and args.device == "cuda":      # torchrun: one process per GPU
+        args.device = f"cuda:{os.environ['LOCAL_RANK']}"
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     from .helper import RegionEHelper
 
     synthetic = args.model_path.startswith("synthetic")
@@ -236,8 +255,9 @@ def main(argv=None) -> int:
 
     if not args.evaluation:                                            # main.py:41-76
         os.makedirs(args.output_dir, exist_ok=True)
-        metadata = _read_jsonl(args.image_path)
+        metadata = _shard(_read_jsonl(args.image_path))
         warmup()
+        t_all = time.time()
         for index, data in enumerate(metadata):
             print(f"[{index + 1} / {len(metadata)}] Reference Image: {data['key']}.png, "
                   f"Instruction: {data['instruction']}")
@@ -245,6 +265,8 @@ def main(argv=None) -> int:
             print(f"Time consuming: {dt}s")
             save(result, os.path.join(args.output_dir, os.path.basename(data["key"])))
             print(f"Image has been saved to {args.output_dir}")
+        if metadata:
+            print(f"rank {os.environ.get('RANK', '0')}: {len(metadata)} images in {time.time() - t_all:.3f}s")
         return 0
     for task in sorted(os.listdir(args.image_path)):                   # main.py:78-129
         image_path = os.path.join(args.image_path, task)
@@ -252,7 +274,7 @@ def main(argv=None) -> int:
             continue
         output_dir = os.path.join(args.output_dir, task)
         os.makedirs(f"{output_dir}/generation", exist_ok=True)
-        metadata = _read_jsonl(f"{image_path}/metadata.jsonl")
+        metadata = _shard(_read_jsonl(f"{image_path}/metadata.jsonl"))
         warmup()
         prefix_prompt, time_consuming = {}, []
         for idx, data in enumerate(metadata):
@@ -263,11 +285,12 @@ def main(argv=None) -> int:
             time_consuming.append(dt)
             where = save(result, f"{output_dir}/generation/{data['key']}")
             print(f"[task:{task} {idx + 1}/{len(metadata)}] {where}, save! cosuming:{dt}s")
-        with open(f"{output_dir}/time_consuming.json", "w") as f:
+        suffix = f".rank{os.environ['RANK']}" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else ""
+        with open(f"{output_dir}/time_consuming{suffix}.json", "w") as f:
             json.dump({"num_item": len(time_consuming),
                        "ave_time_consuming": sum(time_consuming) / max(len(time_consuming), 1),
                        "time_consuming_list": time_consuming}, f, indent=4)
-        with open(f"{output_dir}/metadata.json", "w") as f:
+        with open(f"{output_dir}/metadata{suffix}.json", "w") as f:
             json.dump(prefix_prompt, f, indent=4)
     return 0
 

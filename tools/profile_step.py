@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--full", type=int, default=2)
     ap.add_argument("--region", type=int, default=2)
     ap.add_argument("--edited", type=int, default=1100)
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the LAST step of each kind (ncu --profile-from-start off)")
     args = ap.parse_args()
     from regione_b200 import synthetic as syn
     from regione_b200.engine import FluxEngine
@@ -42,9 +44,14 @@ def main():
                         ("REGION", args.region, lambda: eng.step(x_reg, edited, 920.0, edited.numel()))):
         for i in range(n):
             torch.cuda.synchronize()
+            ranged = args.profiler_range and i == n - 1
+            if ranged:
+                torch.cuda.profiler.start()
             t0 = time.perf_counter()
             fn()
             torch.cuda.synchronize()
+            if ranged:
+                torch.cuda.profiler.stop()
             print(f"{name} step {i}: {(time.perf_counter() - t0) * 1e3:.2f} ms")
     eng.close()
 
