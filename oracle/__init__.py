@@ -16,7 +16,11 @@ What is restated here and how it is pinned:
 * flux.py        the FLUX.1-Kontext DiT (diffusers FluxTransformer2DModel, absent from /root/reference and from this
                  image) restated from its published architecture, plus the reference's forward / attention processor
                  (inplace.py:413-576, 694-824) with the pre-norm/pre-RoPE K/V cache semantics and the fp16 round trip
-                 of `_partially_linear` (fused_kernels.py:80). PARITY UNPINNED: the reference owns no test, golden
-                 vector or fixture for this path and diffusers cannot be imported.
+                 of `_partially_linear` (fused_kernels.py:80). PARITY UNPINNED w.r.t. the reference: it owns no test,
+                 golden vector or fixture for this path and diffusers cannot be imported. Cross-pinned instead against
+                 two independent implementations that do exist in this image: the original black-forest-labs/FLUX
+                 blocks vendored by torchtitan (tests/test_oracle_vs_bfl_flux.py: double / single block, rotary
+                 table, time embedding agree to 2e-4 in fp32 under diffusers' weight mapping) and, for the attention
+                 op, the reference's own third-party kernel flash_attn_func (tests/test_kernels_gpu.py).
 * loop.py        the denoising loop and the patched scheduler step (inplace.py:287-392, 594-691).
 """

@@ -194,6 +194,23 @@ def test_attention_matches_exact_softmax(Sq, Skv, H):
     assert rel_l2(o, ref) <= 6e-3                                  # bf16 P and bf16 output
 
 
+@pytest.mark.parametrize("Sq,Skv,H", [(1576, 8704, 4), (8704, 8704, 2), (333, 1000, 3)])
+def test_attention_matches_the_reference_s_flash_attn_func(Sq, Skv, H):
+    """The reference calls flash-attn's `flash_attn_func(q, k, v, causal=False)` at inplace.py:796-801 (README pins
+    flash-attn v2.8.2; this image has 2.8.3): the same call, on the same inputs, is the checker here — a pin of the
+    attention op against the reference's own third-party kernel rather than against the restated oracle."""
+    flash_attn = pytest.importorskip("flash_attn")
+    from regione_b200 import ops
+    g = _gen(9)
+    q = torch.randn(Sq, H * 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(Skv, H * 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(Skv, H * 128, device="cuda", generator=g).bfloat16()
+    o = ops.attention(q, k, v, H)
+    ref = flash_attn.flash_attn_func(q.view(1, Sq, H, 128), k.view(1, Skv, H, 128), v.view(1, Skv, H, 128),
+                                     causal=False).reshape(Sq, H * 128)
+    assert rel_l2(o, ref) <= 6e-3
+
+
 def test_attention_strided_output_and_row_independence():
     """Output written into a wider buffer (the engine's [S, D + 4D] layout); untouched columns stay untouched and
     each query row depends only on its own query (permutation equivariance)."""
