@@ -12,7 +12,7 @@ for r in data:
         continue
     v = float(r[vi].replace(",", ""))
     ms = v / 1e6 if r[ui].startswith("n") else (v / 1e3 if r[ui].startswith("u") else v)
-    name = re.sub(r"\(.*$", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
+    name = re.sub(r"\(.*$", "", r[ki]).replace("void ", "").replace("<unnamed>::", "").replace("unnamed>::", "")
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += ms
