@@ -300,7 +300,7 @@ struct rge_handle {
   std::vector<const void*> gw, dw, sw;
   bool finalized = false;
   std::vector<char> begun;
-  std::vector<int> Tp;   // text length of each pass (<= T); Step1X-Edit v1p2 runs cond / uncond prompts of different length
+  std::vector<int> Tp;   // text length of each pass (<= T): Step1X-Edit v1p2 prompts differ in length
   // workspaces
   bf16 *h = nullptr, *n = nullptr, *q = nullptr, *big = nullptr;
   bf16 *kcache = nullptr, *vcache = nullptr;
@@ -379,7 +379,7 @@ int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_
   for (int i = 0; i < n; ++i)
     if (a[i].M > 0) work += 2.0 * a[i].M * (double)a[i].N * a[i].K;
   if (work == 0) return RGE_OK;
-  ProfScope prof(st, PC_GEMM, work, a[0].M, -n, a[0].K);   // N < 0 marks a group of |N| members in the timeline
+  ProfScope prof(st, PC_GEMM, work, a[0].M, n == 1 ? a[0].N : -n, a[0].K);   // N < 0: a group of |N| members
   RGE_LAUNCH(launch_gemm_group(a, n, sm_cap > 0 ? sm_cap : h->num_sms, st));
   return RGE_OK;
 }
@@ -389,6 +389,244 @@ int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_
     int _r = (expr);             \
     if (_r != RGE_OK) return _r; \
   } while (0)
+
+// One transformer forward's block stack: the launch sequences of a double-stream block and of a
+// single-stream block (App. B-2), each in two flavours - fan-out over the library's side streams (default) and one
+// grouped launch per stage (RGE_GROUPED=1, REGION-sized steps only).
+struct StepRun {
+  rge_handle* h;
+  cudaStream_t st, sT, sK, sV, sTK, sTV;
+  int pass, D, Dm, T, S, M, MA;
+  long ldb;                 // `big`: attention output in columns [0, D), MLP hidden in [D, D + Dm)
+  const float2* rope;
+  bf16 *x_img, *n_img_p, *big_img;
+  int idle_sms;             // SMs the last (partial) wave of the attention grid leaves idle
+  bool fill_tail;           // ... and whether the single blocks' MLP-up GEMM runs there beside attention
+
+  StepRun(rge_handle* h_, cudaStream_t st_, int pass_, int T_, int M_)
+      : h(h_), st(st_), pass(pass_), D(h_->D), Dm(h_->Dm), T(T_), S(T_ + h_->L + h_->C), M(M_), MA(T_ + M_) {
+    ldb = D + Dm;
+    rope = h->rope + (size_t)pass * h->S * 64;
+    x_img = h->h + (size_t)T * D;
+    n_img_p = h->n + (size_t)T * D;
+    big_img = h->big + (size_t)T * ldb;
+    // side streams: sT carries the text chain of the double blocks (and the MLP of the single blocks), sK / sV the
+    // image K and V projections, sTK / sTV the text K and V projections
+    const bool fan = h->fanout;
+    sT = fan ? h->aux[0] : st; sK = fan ? h->aux[1] : st; sV = fan ? h->aux[2] : st;
+    sTK = fan ? h->aux[3] : st; sTV = fan ? h->aux[4] : st;
+    // the MLP-up GEMM fits into the idle SMs if it takes about one attention-CTA time there (per-SM rates of the two
+    // kernels are comparable)
+    const int n_attn_ctas = ((MA + 255) / 256) * h->H;
+    const int attn_tail = n_attn_ctas % h->num_sms;
+    idle_sms = attn_tail ? h->num_sms - attn_tail : 0;
+    fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 &&
+                2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * 4.0 * 256.0 * S * 128.0;
+  }
+
+  // makes `to` wait for everything enqueued on `from` so far
+  cudaError_t link(cudaStream_t from, cudaEvent_t ev, cudaStream_t to) const {
+    if (from == to) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(ev, from);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
+  }
+
+  int attention(bf16* kc, bf16* vc, cudaStream_t sa) const {
+    AttnArgs at;
+    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
+    at.Sq = MA; at.Skv = S; at.H = h->H;
+    ProfScope prof(sa, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H, at.Sq, at.Skv, at.H);
+    RGE_LAUNCH(launch_attention(at, sa));
+    return RGE_OK;
+  }
+
+  // ---- the GEMMs of a double block (b) / single block (b); k / v rows are scattered into the cache at T + sel[m]
+  GemmArgs img_q(int b) const {
+    return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, T, 0,
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T);
+  }
+  GemmArgs img_k(int b, bf16* kc) const {
+    return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_img, T, 0,
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T);
+  }
+  GemmArgs img_v(int b, bf16* vc) const {
+    return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T, 0);
+  }
+  // text stream q / k / v: recomputed every step (the reference does not cache text K/V)
+  GemmArgs txt_q(int b) const {
+    return mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0,
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0);
+  }
+  GemmArgs txt_k(int b, bf16* kc) const {
+    return mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D, nullptr, 0, 0,
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0);
+  }
+  GemmArgs txt_v(int b, bf16* vc) const {
+    return mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0, 0);
+  }
+  // out projections and feed-forward halves with gate * (.) + residual fused
+  GemmArgs img_out(int b, const bf16* gate) const {
+    return mk(big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D, nullptr, 0, 0,
+              gate, x_img, D);
+  }
+  GemmArgs txt_out(int b, const bf16* gate) const {
+    return mk(h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h, D, nullptr,
+              0, 0, gate, h->h, D);
+  }
+  GemmArgs img_up(int b) const {
+    return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb, nullptr, 0,
+              D);
+  }
+  GemmArgs txt_up(int b) const {
+    return mk(h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb, nullptr, 0, D);
+  }
+  GemmArgs img_down(int b, const bf16* gate) const {
+    return mk(big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES, x_img, D,
+              nullptr, 0, 0, gate, x_img, D);
+  }
+  GemmArgs txt_down(int b, const bf16* gate) const {
+    return mk(h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES, h->h, D,
+              nullptr, 0, 0, gate, h->h, D);
+  }
+  // single block on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
+  GemmArgs s_q(int b) const {
+    return mk(h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0, nullptr,
+              nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0);
+  }
+  GemmArgs s_k(int b, bf16* kc) const {
+    return mk(h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all, 0, 0, nullptr,
+              nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0);
+  }
+  GemmArgs s_v(int b, bf16* vc) const {
+    return mk(h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0, 0);
+  }
+  GemmArgs s_mlp(int b) const {
+    return mk(h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr, 0, D);
+  }
+  GemmArgs s_out(int b, const bf16* gate) const {
+    return mk(h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D, nullptr, 0,
+              0, gate, h->h, D);
+  }
+  int one(cudaStream_t s, const GemmArgs& a, int sm_cap = 0) const { return gemm_group(h, s, &a, 1, sm_cap); }
+
+  // adaLN vectors of a double block: image stream at mod, text stream at mod + 6 D; each shift, scale, gate x 2
+  int double_block_fanout(int b, int layer, const bf16* mod) const {
+    const bf16* cm = mod + 6 * D;
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    // image chain on `st`, text chain on sT, joined around attention
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + D, mod, n_img_p, D, M, D, st));
+    RGE_CUDA(link(st, h->ev_main, sK));
+    RGE_CUDA(link(st, h->ev_main, sV));
+    RGE_TRY(one(st, img_q(b)));
+    RGE_TRY(one(sK, img_k(b, kc)));
+    RGE_TRY(one(sV, img_v(b, vc)));
+    // the three text projections are small (T rows): on one stream they would run back to back on a mostly idle GPU
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
+    RGE_CUDA(link(sT, h->ev_txt, sTK));
+    RGE_CUDA(link(sT, h->ev_txt, sTV));
+    RGE_TRY(one(sT, txt_q(b)));
+    RGE_TRY(one(sTK, txt_k(b, kc)));
+    RGE_TRY(one(sTV, txt_v(b, vc)));
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    RGE_CUDA(link(sK, h->ev_aux[1], st));
+    RGE_CUDA(link(sV, h->ev_aux[2], st));
+    RGE_CUDA(link(sTK, h->ev_aux[3], st));
+    RGE_CUDA(link(sTV, h->ev_aux[4], st));
+    RGE_TRY(attention(kc, vc, st));
+    RGE_CUDA(link(st, h->ev_main, sT));
+    // out projection, LayerNorm, feed-forward: each stream on its own chain
+    RGE_TRY(one(st, img_out(b, mod + 2 * D)));
+    RGE_TRY(one(sT, txt_out(b, cm + 2 * D)));
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + 4 * D, mod + 3 * D, n_img_p, D, M, D, st));
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + 4 * D, cm + 3 * D, h->n, D, T, D, sT));
+    RGE_TRY(one(st, img_up(b)));
+    RGE_TRY(one(sT, txt_up(b)));
+    RGE_TRY(one(st, img_down(b, mod + 5 * D)));
+    RGE_TRY(one(sT, txt_down(b, cm + 5 * D)));
+    return RGE_OK;
+  }
+
+  int double_block_grouped(int b, int layer, const bf16* mod) const {
+    const bf16* cm = mod + 6 * D;
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + D, mod, n_img_p, D, M, D, st));
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, st));
+    const GemmArgs qkv[6] = {img_q(b), img_k(b, kc), img_v(b, vc), txt_q(b), txt_k(b, kc), txt_v(b, vc)};
+    RGE_TRY(gemm_group(h, st, qkv, 6));
+    RGE_TRY(attention(kc, vc, st));
+    const GemmArgs outp[2] = {img_out(b, mod + 2 * D), txt_out(b, cm + 2 * D)};
+    RGE_TRY(gemm_group(h, st, outp, 2));
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + 4 * D, mod + 3 * D, n_img_p, D, M, D, st));
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + 4 * D, cm + 3 * D, h->n, D, T, D, st));
+    const GemmArgs up[2] = {img_up(b), txt_up(b)};
+    RGE_TRY(gemm_group(h, st, up, 2));
+    const GemmArgs down[2] = {img_down(b, mod + 5 * D), txt_down(b, cm + 5 * D)};
+    RGE_TRY(gemm_group(h, st, down, 2));
+    return RGE_OK;
+  }
+
+  // attention on the high-priority stream and the MLP-up GEMM, capped to the SMs the last attention wave leaves idle,
+  // both start once `ev_q` (and, in the fan-out, the K / V events already recorded) are reached
+  int attention_beside_mlp(int b, bf16* kc, bf16* vc, bool wait_kv) const {
+    RGE_CUDA(cudaEventRecord(h->ev_q, st));
+    for (cudaStream_t s2 : {h->sattn, sT}) {
+      RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_q, 0));
+      if (wait_kv) {
+        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[1], 0));
+        RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[2], 0));
+      }
+    }
+    RGE_TRY(attention(kc, vc, h->sattn));
+    RGE_TRY(one(sT, s_mlp(b), idle_sms));
+    RGE_CUDA(link(h->sattn, h->ev_attn, st));
+    return RGE_OK;
+  }
+
+  // adaLN vectors of a single block at mod: shift, scale, gate
+  int single_block_fanout(int b, int layer, const bf16* mod) const {
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, mod + D, mod, h->n, D, MA, D, st));
+    if (!fill_tail) RGE_CUDA(link(st, h->ev_main, sT));
+    RGE_CUDA(link(st, h->ev_main, sK));
+    RGE_CUDA(link(st, h->ev_main, sV));
+    RGE_TRY(one(st, s_q(b)));
+    RGE_TRY(one(sK, s_k(b, kc)));
+    RGE_TRY(one(sV, s_v(b, vc)));
+    if (!fill_tail) {
+      // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT when attention
+      // starts: its CTAs and the attention CTAs share the SMs, which fills the partial last wave of either kernel
+      RGE_TRY(one(sT, s_mlp(b)));
+      RGE_CUDA(link(sK, h->ev_aux[1], st));
+      RGE_CUDA(link(sV, h->ev_aux[2], st));
+      RGE_TRY(attention(kc, vc, st));
+    } else {
+      RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
+      RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
+      RGE_TRY(attention_beside_mlp(b, kc, vc, true));
+    }
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    return one(st, s_out(b, mod + 2 * D));
+  }
+
+  int single_block_grouped(int b, int layer, const bf16* mod) const {
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, mod + D, mod, h->n, D, MA, D, st));
+    const GemmArgs proj[4] = {s_q(b), s_k(b, kc), s_v(b, vc), s_mlp(b)};
+    if (!fill_tail) {
+      RGE_TRY(gemm_group(h, st, proj, 4));
+      RGE_TRY(attention(kc, vc, st));
+    } else {
+      RGE_TRY(gemm_group(h, st, proj, 3));
+      RGE_TRY(attention_beside_mlp(b, kc, vc, false));
+      RGE_CUDA(link(sT, h->ev_aux[0], st));
+    }
+    return one(st, s_out(b, mod + 2 * D));
+  }
+};
 
 }  // namespace
 
@@ -400,7 +638,8 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
     return fail(RGE_ERR_UNSUPPORTED, "rge_create: head_dim must be 128 (dim %d heads %d)", cfg->dim, cfg->heads);
   if (cfg->dim > 4096 || cfg->pooled_dim > 4096 || cfg->dim % 256)
     return fail(RGE_ERR_UNSUPPORTED, "rge_create: dim must be a multiple of 256 and <= 4096");
-  if (cfg->in_channels % 32 || cfg->ctx_dim % 8 || cfg->pooled_dim % 8 || cfg->pooled_dim < 0 || cfg->ctx_dim < 0 || cfg->txt_len < 0 || cfg->lat_len <= 0 ||
+  if (cfg->in_channels % 32 || cfg->ctx_dim % 8 || cfg->pooled_dim % 8 || cfg->pooled_dim < 0 || cfg->ctx_dim < 0 ||
+      cfg->txt_len < 0 || cfg->lat_len <= 0 ||
       cfg->cond_len < 0 || cfg->n_pass < 1 || cfg->mlp_ratio < 1 || cfg->n_double < 0 || cfg->n_single < 0)
     return fail(RGE_ERR_INVALID, "rge_create: bad shape");
   RGE_CUDA(cudaSetDevice(cfg->device));
@@ -648,211 +887,21 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   RGE_TRY(gemm(h, st, (const bf16*)x_in, h->cfg.in_channels, M, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
                h->G(RGE_G_X_EMBED_B), D, EPI_STORE, h->h, D, nullptr, T, 0));
 
-  bf16* x_img = h->h + (size_t)T * D;
-  bf16* n_img_p = h->n + (size_t)T * D;
-  bf16* big_img = h->big + (size_t)T * ldb;
+  StepRun r(h, st, pass, T, M);
   const bf16* mod = h->mods;
   int layer = 0;
-  // side streams: sT carries the text chain of the double blocks (and the MLP of the single blocks), sK / sV the
-  // K and V projections; `link(from, ev, to)` makes `to` wait for everything enqueued on `from` so far
-  const bool fan = h->fanout;
-  cudaStream_t sT = fan ? h->aux[0] : st, sK = fan ? h->aux[1] : st, sV = fan ? h->aux[2] : st;
-  cudaStream_t sTK = fan ? h->aux[3] : st, sTV = fan ? h->aux[4] : st;
-  auto link = [&](cudaStream_t from, cudaEvent_t ev, cudaStream_t to) -> cudaError_t {
-    if (from == to) return cudaSuccess;
-    cudaError_t e = cudaEventRecord(ev, from);
-    return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
-  };
-  auto attention = [&](bf16* kc, bf16* vc, cudaStream_t sa) -> int {
-    AttnArgs at;
-    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
-    at.Sq = MA; at.Skv = S; at.H = h->H;
-    ProfScope prof(sa, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H, at.Sq, at.Skv, at.H);
-    RGE_LAUNCH(launch_attention(at, sa));
-    return RGE_OK;
-  };
-  // SMs the last (partial) wave of the attention grid leaves idle, and whether the single blocks' MLP-up GEMM fits
-  // into them within about one attention-CTA time (per-SM rates of the two kernels are comparable)
-  const int n_attn_ctas = ((MA + 255) / 256) * h->H;
-  const int attn_tail = n_attn_ctas % h->num_sms;
-  const int idle_sms = attn_tail ? h->num_sms - attn_tail : 0;
-  const bool fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 &&
-                         2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * 4.0 * 256.0 * S * 128.0;
-  // A step whose widest GEMM (MA rows) stays below the CTA-pair kernel's threshold is a REGION step (or a small model):
-  // there every stage of a block is ONE grouped launch on `st` (no side streams, no events). FULL steps keep the
-  // fan-out below, where each large GEMM fills the GPU by itself.
-  const bool grouped = h->grouped && MA < 2048;
-  if (grouped) {
-    for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
-      const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
-                 *g_mlp = mod + 5 * D;
-      const bf16* cm = mod + 6 * D;
-      const bf16 *csh_msa = cm, *csc_msa = cm + D, *cg_msa = cm + 2 * D, *csh_mlp = cm + 3 * D, *csc_mlp = cm + 4 * D,
-                 *cg_mlp = cm + 5 * D;
-      bf16* kc = h->kc(pass, layer);
-      bf16* vc = h->vc(pass, layer);
-      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
-      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, st));
-      const GemmArgs qkv[6] = {
-          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, T, 0, nullptr,
-             nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T),
-          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_img, T, 0, nullptr,
-             nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T),
-          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T, 0),
-          mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0,
-             nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0),
-          mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D, nullptr, 0, 0,
-             nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0),
-          mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0, 0)};
-      RGE_TRY(gemm_group(h, st, qkv, 6));
-      RGE_TRY(attention(kc, vc, st));
-      const GemmArgs outp[2] = {
-          mk(big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D, nullptr, 0, 0,
-             g_msa, x_img, D),
-          mk(h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h, D, nullptr, 0,
-             0, cg_msa, h->h, D)};
-      RGE_TRY(gemm_group(h, st, outp, 2));
-      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
-      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, st));
-      const GemmArgs up[2] = {
-          mk(n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb, nullptr, 0, D),
-          mk(h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb, nullptr, 0, D)};
-      RGE_TRY(gemm_group(h, st, up, 2));
-      const GemmArgs down[2] = {
-          mk(big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES, x_img, D,
-             nullptr, 0, 0, g_mlp, x_img, D),
-          mk(h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES, h->h, D,
-             nullptr, 0, 0, cg_mlp, h->h, D)};
-      RGE_TRY(gemm_group(h, st, down, 2));
-    }
-    for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
-      const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
-      bf16* kc = h->kc(pass, layer);
-      bf16* vc = h->vc(pass, layer);
-      RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
-      const GemmArgs proj[4] = {
-          mk(h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0, nullptr,
-             nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0),
-          mk(h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all, 0, 0, nullptr,
-             nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0),
-          mk(h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0, 0),
-          mk(h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb, nullptr, 0, D)};
-      if (!fill_tail) {
-        RGE_TRY(gemm_group(h, st, proj, 4));
-        RGE_TRY(attention(kc, vc, st));
-      } else {
-        // attention (high priority) and the MLP GEMM (capped to the SMs its last wave leaves idle) start together
-        RGE_TRY(gemm_group(h, st, proj, 3));
-        RGE_CUDA(cudaEventRecord(h->ev_q, st));
-        RGE_CUDA(cudaStreamWaitEvent(h->sattn, h->ev_q, 0));
-        RGE_CUDA(cudaStreamWaitEvent(sT, h->ev_q, 0));
-        RGE_TRY(attention(kc, vc, h->sattn));
-        RGE_TRY(gemm_group(h, sT, proj + 3, 1, idle_sms));
-        RGE_CUDA(link(h->sattn, h->ev_attn, st));
-        RGE_CUDA(link(sT, h->ev_aux[0], st));
-      }
-      RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
-                   nullptr, 0, 0, g, h->h, D));
-    }
-  } else {
-    // ---- double-stream blocks: image chain on `st`, text chain on sT, joined around attention
-    if (h->cfg.n_double > 0) RGE_CUDA(link(st, h->ev_main, sT));
-    for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
-      const bf16 *sh_msa = mod, *sc_msa = mod + D, *g_msa = mod + 2 * D, *sh_mlp = mod + 3 * D, *sc_mlp = mod + 4 * D,
-                 *g_mlp = mod + 5 * D;
-      const bf16* cm = mod + 6 * D;
-      const bf16 *csh_msa = cm, *csc_msa = cm + D, *cg_msa = cm + 2 * D, *csh_mlp = cm + 3 * D, *csc_mlp = cm + 4 * D,
-                 *cg_mlp = cm + 5 * D;
-      bf16* kc = h->kc(pass, layer);
-      bf16* vc = h->vc(pass, layer);
-      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_msa, sh_msa, n_img_p, D, M, D, st));
-      RGE_CUDA(link(st, h->ev_main, sK));
-      RGE_CUDA(link(st, h->ev_main, sV));
-      // image stream q/k/v; k,v rows scattered into the cache at T + sel[m]
-      RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr,
-                   T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T));
-      RGE_TRY(gemm(h, sK, n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D,
-                   h->sel_img, T, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T));
-      RGE_TRY(gemm(h, sV, n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T,
-                   0));
-      // text stream q/k/v (recomputed every step: the reference does not cache text K/V)
-      // the three text projections are small (T rows): on one stream they would run back to back on a mostly idle GPU
-      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_msa, csh_msa, h->n, D, T, D, sT));
-      RGE_CUDA(link(sT, h->ev_txt, sTK));
-      RGE_CUDA(link(sT, h->ev_txt, sTV));
-      RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D,
-                   nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0));
-      RGE_TRY(gemm(h, sTK, h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D,
-                   nullptr, 0, 0, nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0));
-      RGE_TRY(gemm(h, sTV, h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr,
-                   0, 0));
-      RGE_CUDA(link(sT, h->ev_aux[0], st));
-      RGE_CUDA(link(sK, h->ev_aux[1], st));
-      RGE_CUDA(link(sV, h->ev_aux[2], st));
-      RGE_CUDA(link(sTK, h->ev_aux[3], st));
-      RGE_CUDA(link(sTV, h->ev_aux[4], st));
-      RGE_TRY(attention(kc, vc, st));
-      RGE_CUDA(link(st, h->ev_main, sT));
-      // out projections with gate * (.) + residual fused, then the feed-forward; each stream on its own chain
-      RGE_TRY(gemm(h, st, big_img, ldb, M, D, h->Dw(b, RGE_D_OUT_W), h->Dw(b, RGE_D_OUT_B), D, EPI_GATE_RES, x_img, D,
-                   nullptr, 0, 0, g_msa, x_img, D));
-      RGE_TRY(gemm(h, sT, h->big, ldb, T, D, h->Dw(b, RGE_D_ADD_OUT_W), h->Dw(b, RGE_D_ADD_OUT_B), D, EPI_GATE_RES, h->h,
-                   D, nullptr, 0, 0, cg_msa, h->h, D));
-      RGE_LAUNCH(launch_ln_modulate(x_img, D, sc_mlp, sh_mlp, n_img_p, D, M, D, st));
-      RGE_LAUNCH(launch_ln_modulate(h->h, D, csc_mlp, csh_mlp, h->n, D, T, D, sT));
-      RGE_TRY(gemm(h, st, n_img_p, D, M, D, h->Dw(b, RGE_D_FF_UP_W), h->Dw(b, RGE_D_FF_UP_B), Dm, EPI_GELU, big_img, ldb,
-                   nullptr, 0, D));
-      RGE_TRY(gemm(h, sT, h->n, D, T, D, h->Dw(b, RGE_D_FFC_UP_W), h->Dw(b, RGE_D_FFC_UP_B), Dm, EPI_GELU, h->big, ldb,
-                   nullptr, 0, D));
-      RGE_TRY(gemm(h, st, big_img + D, ldb, M, Dm, h->Dw(b, RGE_D_FF_DOWN_W), h->Dw(b, RGE_D_FF_DOWN_B), D, EPI_GATE_RES,
-                   x_img, D, nullptr, 0, 0, g_mlp, x_img, D));
-      RGE_TRY(gemm(h, sT, h->big + D, ldb, T, Dm, h->Dw(b, RGE_D_FFC_DOWN_W), h->Dw(b, RGE_D_FFC_DOWN_B), D, EPI_GATE_RES,
-                   h->h, D, nullptr, 0, 0, cg_mlp, h->h, D));
-    }
-    if (h->cfg.n_double > 0) RGE_CUDA(link(sT, h->ev_aux[0], st));
-    // ---- single-stream blocks on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
-    for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
-      const bf16 *sh = mod, *sc = mod + D, *g = mod + 2 * D;
-      bf16* kc = h->kc(pass, layer);
-      bf16* vc = h->vc(pass, layer);
-      RGE_LAUNCH(launch_ln_modulate(h->h, D, sc, sh, h->n, D, MA, D, st));
-      if (!fill_tail) RGE_CUDA(link(st, h->ev_main, sT));
-      RGE_CUDA(link(st, h->ev_main, sK));
-      RGE_CUDA(link(st, h->ev_main, sV));
-      RGE_TRY(gemm(h, st, h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0,
-                   0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0));
-      RGE_TRY(gemm(h, sK, h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all,
-                   0, 0, nullptr, nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0));
-      RGE_TRY(gemm(h, sV, h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0,
-                   0));
-      if (!fill_tail) {
-        RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
-                     nullptr, 0, D));
-        RGE_CUDA(link(sK, h->ev_aux[1], st));
-        RGE_CUDA(link(sV, h->ev_aux[2], st));
-        RGE_TRY(attention(kc, vc, st));
-        // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT: its CTAs and
-        // the attention CTAs share the SMs, which fills the partial last wave of either kernel
-      } else {
-        // attention (high priority) and the MLP GEMM (capped to the idle SMs) both start once q, k and v are done
-        RGE_CUDA(cudaEventRecord(h->ev_q, st));
-        RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
-        RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
-        for (cudaStream_t s2 : {h->sattn, sT}) {
-          RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_q, 0));
-          RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[1], 0));
-          RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[2], 0));
-        }
-        RGE_TRY(attention(kc, vc, h->sattn));
-        RGE_TRY(gemm(h, sT, h->n, D, MA, D, h->Sw(b, RGE_S_MLP_W), h->Sw(b, RGE_S_MLP_B), Dm, EPI_GELU, h->big, ldb,
-                     nullptr, 0, D, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, idle_sms));
-        RGE_CUDA(link(h->sattn, h->ev_attn, st));
-      }
-      RGE_CUDA(link(sT, h->ev_aux[0], st));
-      RGE_TRY(gemm(h, st, h->big, ldb, MA, D + Dm, h->Sw(b, RGE_S_OUT_W), h->Sw(b, RGE_S_OUT_B), D, EPI_GATE_RES, h->h, D,
-                   nullptr, 0, 0, g, h->h, D));
-    }
-  }
+  // A step whose widest GEMM (T + M rows) stays below the CTA-pair kernel's threshold is a REGION step (or a small
+  // model): with RGE_GROUPED=1 every stage of a block is then ONE grouped launch on `st`. Otherwise the independent
+  // GEMMs of a stage fan out over the side streams (the default: see rge_handle::grouped).
+  const bool grouped = h->grouped && r.MA < 2048;
+  if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(st, h->ev_main, r.sT));
+  for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D)
+    RGE_TRY(grouped ? r.double_block_grouped(b, layer, mod) : r.double_block_fanout(b, layer, mod));
+  if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(r.sT, h->ev_aux[0], st));
+  for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D)
+    RGE_TRY(grouped ? r.single_block_grouped(b, layer, mod) : r.single_block_fanout(b, layer, mod));
+  bf16* x_img = r.x_img;
+  bf16* n_img_p = r.n_img_p;
   // ---- norm_out (scale first, then shift) + proj_out on the noise rows only (App. C-9)
   RGE_LAUNCH(launch_ln_modulate(x_img, D, mod, mod + D, n_img_p, D, n_out, D, st));
   RGE_TRY(gemm(h, st, n_img_p, D, n_out, D, h->G(RGE_G_PROJ_OUT_W), h->G(RGE_G_PROJ_OUT_B), h->cfg.in_channels,

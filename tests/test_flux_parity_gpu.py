@@ -110,3 +110,15 @@ def test_wider_model_three_heads():
     from regione_b200 import synthetic as syn
     arch = dict(syn.TINY, dim=768, heads=6, n_double=1, n_single=2, ctx_dim=256)
     _check(*_run_both(arch, (16, 16), 64, 0.25, DEFAULT, seed=13))
+
+
+@pytest.mark.parametrize("env", [{"RGE_GROUPED": "1"}, {"RGE_GROUPED": "1", "RGE_FILL_ATTN_TAIL": "0"},
+                                 {"RGE_FILL_ATTN_TAIL": "0"}, {"RGE_NO_FANOUT": "1"}])
+def test_launch_schedule_variants_give_the_same_image(env, monkeypatch):
+    """The engine's launch-schedule knobs (read at rge_create): one grouped launch per stage, attention-tail fill off,
+    no side streams. They only reorder independent launches, so every one must pass the same parity gate."""
+    from regione_b200 import synthetic as syn
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _check(*_run_both(syn.TINY, (16, 16), 32, 0.25, DEFAULT))
+    _check(*_run_both(syn.TINY, (12, 20), 40, 0.0, DEFAULT, seed=5))      # empty edited set through the grouped path
