@@ -2,7 +2,8 @@
 
 Reference: RegionE/FluxKontext/inplace.py:229-244 (sigmas, mu), :295-313 (AVDC), utils.py:38-48 (calculate_shift).
 `FlowMatchEulerDiscreteScheduler.set_timesteps` is diffusers code (not in /root/reference, not installed): restated
-from its published algorithm (dynamic exponential time shift), parity unpinned for that function.
+from its published algorithm (dynamic exponential time shift); unpinned w.r.t. diffusers, cross-pinned against BFL's own
+sampler schedule (tests/test_oracle_vs_bfl_flux.py).
 """
 from __future__ import annotations
 

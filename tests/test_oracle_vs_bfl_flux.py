@@ -128,3 +128,24 @@ def test_rotary_table_and_time_embedding_match_bfl_flux():
     assert torch.allclose(of.apply_rope(x, (cos, sin)), ref, atol=1e-5)
     t = torch.tensor([0.9356, 0.1047])
     assert torch.allclose(of.timestep_projection(t * 1000), layers.timestep_embedding(t, 256), atol=1e-5)
+
+
+def test_sigma_schedule_matches_bfl_flux_sampling():
+    """The dynamic exponential time shift of diffusers' FlowMatchEulerDiscreteScheduler.set_timesteps (restated in
+    oracle/schedule.py, mirrored by the stand-in scheduler) against BFL's own sampler schedule (get_schedule:
+    linspace(1, 0, N + 1) -> time_shift(mu(seq_len), 1, t)); mu = the reference's calculate_shift."""
+    sampling = pytest.importorskip("torchtitan.experiments.flux.sampling")
+    import numpy as np
+    from oracle.schedule import calculate_shift, flow_match_sigmas
+    from regione_b200 import schedule
+    from regione_b200.standin import FlowMatchEulerDiscreteScheduler
+    for n_tokens in (4096, 4050, 2304, 1024):
+        ref = torch.tensor(sampling.get_schedule(28, n_tokens), dtype=torch.float32)          # 29 values, last 0
+        sig, ts = flow_match_sigmas(28, n_tokens)
+        assert sig.shape == ref.shape and float(sig[-1]) == 0.0
+        assert torch.allclose(sig, ref, atol=2e-6, rtol=0)
+        assert torch.allclose(ts, ref[:-1] * 1000, atol=2e-3, rtol=0)
+        assert calculate_shift(n_tokens) == pytest.approx(sampling.get_lin_function()(n_tokens), abs=1e-12)
+        sch = FlowMatchEulerDiscreteScheduler()
+        schedule.retrieve_timesteps(sch, 28, "cpu", sigmas=np.linspace(1.0, 1 / 28, 28), mu=schedule.calculate_shift(n_tokens))
+        assert torch.equal(sch.sigmas, sig)
