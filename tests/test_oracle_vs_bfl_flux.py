@@ -71,8 +71,27 @@ def test_double_and_single_block_match_bfl_flux():
 
     # ---- double block
     blk = layers.DoubleStreamBlock(D, H, 4.0, qkv_bias=True)
+    blk.load_state_dict(_double_sd(w), strict=True)
+    with torch.no_grad():
+        ref_img, ref_txt = blk(img, txt, vec, pe)
+        got_txt, got_img = oracle.double_block(0, img, txt, vec, rope, rope, st)
+    assert torch.allclose(got_img, ref_img, rtol=2e-4, atol=2e-4), float((got_img - ref_img).abs().max())
+    assert torch.allclose(got_txt, ref_txt, rtol=2e-4, atol=2e-4), float((got_txt - ref_txt).abs().max())
+
+    # ---- single block on [text; image]
+    sb = layers.SingleStreamBlock(D, H, 4.0)
+    sb.load_state_dict(_single_sd(w), strict=True)
+    with torch.no_grad():
+        ref = sb(torch.cat([txt, img], 1), vec, pe)
+        got_txt, got_img = oracle.single_block(0, img, txt, vec, rope, rope, st)
+    got = torch.cat([got_txt, got_img], 1)
+    assert torch.allclose(got, ref, rtol=2e-4, atol=2e-4), float((got - ref).abs().max())
+
+
+def _double_sd(w):
+    """diffusers FluxTransformerBlock parameters -> BFL DoubleStreamBlock state dict (convert_flux_to_diffusers, reversed)."""
     p = "transformer_blocks.0."
-    sd = {
+    return {
         "img_mod.lin.weight": w[p + "norm1.linear.weight"], "img_mod.lin.bias": w[p + "norm1.linear.bias"],
         "txt_mod.lin.weight": w[p + "norm1_context.linear.weight"], "txt_mod.lin.bias": w[p + "norm1_context.linear.bias"],
         "img_attn.qkv.weight": _cat(w, [p + "attn.to_q", p + "attn.to_k", p + "attn.to_v"], ".weight"),
@@ -90,28 +109,68 @@ def test_double_and_single_block_match_bfl_flux():
         "txt_mlp.0.weight": w[p + "ff_context.net.0.proj.weight"], "txt_mlp.0.bias": w[p + "ff_context.net.0.proj.bias"],
         "txt_mlp.2.weight": w[p + "ff_context.net.2.weight"], "txt_mlp.2.bias": w[p + "ff_context.net.2.bias"],
     }
-    blk.load_state_dict(sd, strict=True)
-    with torch.no_grad():
-        ref_img, ref_txt = blk(img, txt, vec, pe)
-        got_txt, got_img = oracle.double_block(0, img, txt, vec, rope, rope, st)
-    assert torch.allclose(got_img, ref_img, rtol=2e-4, atol=2e-4), float((got_img - ref_img).abs().max())
-    assert torch.allclose(got_txt, ref_txt, rtol=2e-4, atol=2e-4), float((got_txt - ref_txt).abs().max())
 
-    # ---- single block on [text; image]
-    sb = layers.SingleStreamBlock(D, H, 4.0)
+
+def _single_sd(w):
     s = "single_transformer_blocks.0."
     names = [s + "attn.to_q", s + "attn.to_k", s + "attn.to_v", s + "proj_mlp"]
-    sb.load_state_dict({
+    return {
         "modulation.lin.weight": w[s + "norm.linear.weight"], "modulation.lin.bias": w[s + "norm.linear.bias"],
         "linear1.weight": _cat(w, names, ".weight"), "linear1.bias": _cat(w, names, ".bias"),
         "linear2.weight": w[s + "proj_out.weight"], "linear2.bias": w[s + "proj_out.bias"],
         "norm.query_norm.weight": w[s + "attn.norm_q.weight"], "norm.key_norm.weight": w[s + "attn.norm_k.weight"],
-    }, strict=True)
+    }
+
+
+def test_whole_forward_matches_bfl_flux_model():
+    """Front and back of the DiT too: x_embedder / context_embedder, time + pooled-text embedding (no guidance
+    embedder in this BFL variant), norm_out (diffusers chunks (scale, shift), BFL (shift, scale): the conversion
+    script swaps the halves of the Linear) and proj_out, around one double and one single block."""
+    model_mod = pytest.importorskip("torchtitan.experiments.flux.model.model")
+    from torchtitan.experiments.flux.model.args import FluxModelArgs
+    w, g = _weights(3)
+    CTX, POOL, CH = 32, 16, 64
+
+    def lin(name, n, k):
+        w[name + ".weight"] = torch.randn(n, k, generator=g) * 0.05
+        w[name + ".bias"] = torch.randn(n, generator=g) * 0.05
+
+    lin("x_embedder", D, CH); lin("context_embedder", D, CTX)
+    lin("time_text_embed.timestep_embedder.linear_1", D, 256); lin("time_text_embed.timestep_embedder.linear_2", D, D)
+    lin("time_text_embed.text_embedder.linear_1", D, POOL); lin("time_text_embed.text_embedder.linear_2", D, D)
+    lin("norm_out.linear", 2 * D, D); lin("proj_out", CH, D)
+    args = FluxModelArgs(in_channels=CH, out_channels=CH, vec_in_dim=POOL, context_in_dim=CTX, hidden_size=D,
+                         num_heads=H, depth=1, depth_single_blocks=1)
+    bfl = model_mod.FluxModel(args)
+    swap = lambda t: torch.cat([t[D:], t[:D]], 0)                              # noqa: E731  (scale, shift) -> (shift, scale)
+    sd = {"img_in.weight": w["x_embedder.weight"], "img_in.bias": w["x_embedder.bias"],
+          "txt_in.weight": w["context_embedder.weight"], "txt_in.bias": w["context_embedder.bias"],
+          "time_in.in_layer.weight": w["time_text_embed.timestep_embedder.linear_1.weight"],
+          "time_in.in_layer.bias": w["time_text_embed.timestep_embedder.linear_1.bias"],
+          "time_in.out_layer.weight": w["time_text_embed.timestep_embedder.linear_2.weight"],
+          "time_in.out_layer.bias": w["time_text_embed.timestep_embedder.linear_2.bias"],
+          "vector_in.in_layer.weight": w["time_text_embed.text_embedder.linear_1.weight"],
+          "vector_in.in_layer.bias": w["time_text_embed.text_embedder.linear_1.bias"],
+          "vector_in.out_layer.weight": w["time_text_embed.text_embedder.linear_2.weight"],
+          "vector_in.out_layer.bias": w["time_text_embed.text_embedder.linear_2.bias"],
+          "final_layer.adaLN_modulation.1.weight": swap(w["norm_out.linear.weight"]),
+          "final_layer.adaLN_modulation.1.bias": swap(w["norm_out.linear.bias"]),
+          "final_layer.linear.weight": w["proj_out.weight"], "final_layer.linear.bias": w["proj_out.bias"]}
+    sd.update({"double_blocks.0." + k: v for k, v in _double_sd(w).items()})
+    sd.update({"single_blocks.0." + k: v for k, v in _single_sd(w).items()})
+    bfl.load_state_dict(sd, strict=True)
+    img_ids = torch.zeros(G * G, 3)
+    img_ids[:, 1] = torch.arange(G * G) // G
+    img_ids[:, 2] = torch.arange(G * G) % G
+    txt_ids = torch.zeros(T, 3)
+    x = torch.randn(1, G * G, CH, generator=g)
+    ctx = torch.randn(1, T, CTX, generator=g)
+    pooled = torch.randn(1, POOL, generator=g)
+    t = torch.tensor([0.9356])
     with torch.no_grad():
-        ref = sb(torch.cat([txt, img], 1), vec, pe)
-        got_txt, got_img = oracle.single_block(0, img, txt, vec, rope, rope, st)
-    got = torch.cat([got_txt, got_img], 1)
-    assert torch.allclose(got, ref, rtol=2e-4, atol=2e-4), float((got - ref).abs().max())
+        ref = bfl(x, img_ids[None], ctx, txt_ids[None], t, pooled)
+        got = of.FluxOracle(w, H, 1, 1, guidance_embeds=False).forward(_state(img_ids), x, ctx, pooled, t, img_ids, txt_ids, None)
+    assert torch.allclose(got, ref, rtol=3e-4, atol=3e-4), float((got - ref).abs().max())
 
 
 def test_rotary_table_and_time_embedding_match_bfl_flux():
