@@ -331,6 +331,10 @@ struct rge_handle {
   // the pre-attention stage gets faster (119 vs 184 us) but the free-running image / text chains after attention,
   // which overlap with the next block in the fan-out, are serialised at every stage.
   bool grouped = false;
+  // RGE_GROUP_QKV=1: keep the fan-out but launch the q / k / v projections of one stream (image, text, single block)
+  // as one grouped launch on that stream's chain: fewer launch + prologue + un-overlapped-epilogue costs (5 - 15 us
+  // each at REGION sizes, profiles/r01_prof_gemm1cta_region_summary.csv) without serialising independent chains.
+  bool group_qkv = false;
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
@@ -508,6 +512,8 @@ struct StepRun {
               0, gate, h->h, D);
   }
   int one(cudaStream_t s, const GemmArgs& a, int sm_cap = 0) const { return gemm_group(h, s, &a, 1, sm_cap); }
+  // grouped q / k / v only where the members take the 1-CTA path anyway (REGION-sized steps, text stream)
+  bool group_qkv() const { return h->group_qkv && h->fanout && MA < 2048; }
 
   // adaLN vectors of a double block: image stream at mod, text stream at mod + 6 D; each shift, scale, gate x 2
   int double_block_fanout(int b, int layer, const bf16* mod) const {
@@ -516,23 +522,32 @@ struct StepRun {
     bf16* vc = h->vc(pass, layer);
     // image chain on `st`, text chain on sT, joined around attention
     RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + D, mod, n_img_p, D, M, D, st));
-    RGE_CUDA(link(st, h->ev_main, sK));
-    RGE_CUDA(link(st, h->ev_main, sV));
-    RGE_TRY(one(st, img_q(b)));
-    RGE_TRY(one(sK, img_k(b, kc)));
-    RGE_TRY(one(sV, img_v(b, vc)));
-    // the three text projections are small (T rows): on one stream they would run back to back on a mostly idle GPU
-    RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
-    RGE_CUDA(link(sT, h->ev_txt, sTK));
-    RGE_CUDA(link(sT, h->ev_txt, sTV));
-    RGE_TRY(one(sT, txt_q(b)));
-    RGE_TRY(one(sTK, txt_k(b, kc)));
-    RGE_TRY(one(sTV, txt_v(b, vc)));
-    RGE_CUDA(link(sT, h->ev_aux[0], st));
-    RGE_CUDA(link(sK, h->ev_aux[1], st));
-    RGE_CUDA(link(sV, h->ev_aux[2], st));
-    RGE_CUDA(link(sTK, h->ev_aux[3], st));
-    RGE_CUDA(link(sTV, h->ev_aux[4], st));
+    if (group_qkv()) {
+      const GemmArgs iq[3] = {img_q(b), img_k(b, kc), img_v(b, vc)};
+      RGE_TRY(gemm_group(h, st, iq, 3));
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
+      const GemmArgs tq[3] = {txt_q(b), txt_k(b, kc), txt_v(b, vc)};
+      RGE_TRY(gemm_group(h, sT, tq, 3));
+      RGE_CUDA(link(sT, h->ev_aux[0], st));
+    } else {
+      RGE_CUDA(link(st, h->ev_main, sK));
+      RGE_CUDA(link(st, h->ev_main, sV));
+      RGE_TRY(one(st, img_q(b)));
+      RGE_TRY(one(sK, img_k(b, kc)));
+      RGE_TRY(one(sV, img_v(b, vc)));
+      // the three text projections are small (T rows): on one stream they would run back to back on a mostly idle GPU
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
+      RGE_CUDA(link(sT, h->ev_txt, sTK));
+      RGE_CUDA(link(sT, h->ev_txt, sTV));
+      RGE_TRY(one(sT, txt_q(b)));
+      RGE_TRY(one(sTK, txt_k(b, kc)));
+      RGE_TRY(one(sTV, txt_v(b, vc)));
+      RGE_CUDA(link(sT, h->ev_aux[0], st));
+      RGE_CUDA(link(sK, h->ev_aux[1], st));
+      RGE_CUDA(link(sV, h->ev_aux[2], st));
+      RGE_CUDA(link(sTK, h->ev_aux[3], st));
+      RGE_CUDA(link(sTV, h->ev_aux[4], st));
+    }
     RGE_TRY(attention(kc, vc, st));
     RGE_CUDA(link(st, h->ev_main, sT));
     // out projection, LayerNorm, feed-forward: each stream on its own chain
@@ -589,6 +604,18 @@ struct StepRun {
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
     RGE_LAUNCH(launch_ln_modulate(h->h, D, mod + D, mod, h->n, D, MA, D, st));
+    if (group_qkv()) {   // q / k / v as one launch on `st`; the MLP GEMM keeps its own stream as below
+      if (!fill_tail) {
+        RGE_CUDA(link(st, h->ev_main, sT));
+        RGE_TRY(one(sT, s_mlp(b)));
+      }
+      const GemmArgs qkv[3] = {s_q(b), s_k(b, kc), s_v(b, vc)};
+      RGE_TRY(gemm_group(h, st, qkv, 3));
+      if (!fill_tail) RGE_TRY(attention(kc, vc, st));
+      else RGE_TRY(attention_beside_mlp(b, kc, vc, false));
+      RGE_CUDA(link(sT, h->ev_aux[0], st));
+      return one(st, s_out(b, mod + 2 * D));
+    }
     if (!fill_tail) RGE_CUDA(link(st, h->ev_main, sT));
     RGE_CUDA(link(st, h->ev_main, sK));
     RGE_CUDA(link(st, h->ev_main, sV));
@@ -693,6 +720,7 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   if (const char* env = getenv("RGE_NO_FANOUT")) h->fanout = env[0] == '0' || env[0] == 0;
   if (const char* env = getenv("RGE_FILL_ATTN_TAIL")) h->fill_attn_tail = env[0] != '0';
   if (const char* env = getenv("RGE_GROUPED")) h->grouped = env[0] != '0';
+  if (const char* env = getenv("RGE_GROUP_QKV")) h->group_qkv = env[0] != '0';
   if (e != cudaSuccess) {
     rge_destroy(h);
     return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));

@@ -113,7 +113,8 @@ def test_wider_model_three_heads():
 
 
 @pytest.mark.parametrize("env", [{"RGE_GROUPED": "1"}, {"RGE_GROUPED": "1", "RGE_FILL_ATTN_TAIL": "0"},
-                                 {"RGE_FILL_ATTN_TAIL": "0"}, {"RGE_NO_FANOUT": "1"}])
+                                 {"RGE_FILL_ATTN_TAIL": "0"}, {"RGE_NO_FANOUT": "1"}, {"RGE_GROUP_QKV": "1"},
+                                 {"RGE_GROUP_QKV": "1", "RGE_FILL_ATTN_TAIL": "0"}])
 def test_launch_schedule_variants_give_the_same_image(env, monkeypatch):
     """The engine's launch-schedule knobs (read at rge_create): one grouped launch per stage, attention-tail fill off,
     no side streams. They only reorder independent launches, so every one must pass the same parity gate."""
