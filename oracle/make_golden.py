@@ -215,10 +215,70 @@ def make_front_end(u):
     return out
 
 
+def make_family_schedules(u):
+    """The 28-step AVDC plan of EVERY family, produced by that family's own loop code: its gamma table
+    (inplace.py:47-50) and its AVDC block (`if MANAGER.current_step <= MANAGER.warmup_step ...` down to
+    `should_cache = True`, found by pattern in RegionE/<Family>/inplace.py) are exec'd step by step, with the refresh
+    bookkeeping of the scheduler (FluxKontext/inplace.py:630-641, identical in every family) and the real
+    FluxKontextManager.step state machine in between. Parameters = the family's plugin defaults (tool/RegionE.py:1-7)
+    plus the demo thresholds of script/*.sh."""
+    import json
+    from oracle.schedule import flow_match_sigmas
+    ns = {}
+    exec(ref_lines(f"{REF}/tool/RegionE.py", 1, 7), ns)
+    defaults = ns["config"]
+    sched_src = ref_lines(f"{REF}/FluxKontext/inplace.py", 630, 641)
+    out = {}
+    for name, d in FAMILY_DIRS.items():
+        src = open(f"{REF}/{d}/inplace.py").read().split("\n")
+        first = next(i for i, line in enumerate(src) if line.startswith("gamma = torch.tensor("))
+        last = next(i for i in range(first, first + 8) if "dtype=torch.float16)" in src[i])
+        gns = {"torch": torch}
+        exec("\n".join(src[first:last + 1]), gns)
+        a0 = next(i for i, line in enumerate(src) if line.strip().startswith("if MANAGER.current_step <= MANAGER.warmup_step"))
+        a1 = next(i for i in range(a0, a0 + 40) if src[i].strip() == "should_cache = True")
+        avdc_src = textwrap.dedent("\n".join(src[a0:a1 + 1]))
+        plans = []
+        for extra in ({}, {"cache_threshold": 0.01}, {"refresh_step": "12,20", "warmup_step": 5, "post_step": 3}):
+            prm = dict(defaults[name], **extra)
+            M = u.FluxKontextManager()
+            M.set_parameters(prm)
+            L = 64
+            sigmas, timesteps = flow_match_sigmas(28, 4096)
+            lat, ids = torch.zeros(1, L, 8), torch.zeros(2 * L, 3)
+            M.refresh(lat, torch.zeros(1, L, 8), ids, torch.zeros(5, 3), 2, 8, 128, 128)
+
+            class _S:
+                pass
+            S = _S()
+            S.sigmas = sigmas
+            env = dict(MANAGER=M, gamma=gns["gamma"], timesteps=timesteps, should_cache=False, accumulate=1, error=0,
+                       self=S, torch=torch)
+            steps = []
+            for i, t in enumerate(timesteps):
+                env.update(i=i, t=t)
+                exec(avdc_src, env)
+                skip = bool(env["should_cache"])
+                steps.append(dict(skip=skip, ratio=float(env["ratio"]) if skip else None))
+                env.update(sigma=sigmas[i], sigma_next=sigmas[i + 1])
+                exec(sched_src, env)
+                if M.current_step == M.warmup_step - 1:
+                    M.edited_ids = torch.arange(0, L, 4).unsqueeze(0)
+                    M.unedited_ids = torch.tensor([j for j in range(L) if j % 4]).unsqueeze(0)
+                lat, ids = M.step(lat, ids)
+            plans.append(dict(params=prm, steps=steps))
+        out[name] = plans
+    with open(os.path.join(OUT, "family_schedules.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     u = load_reference_utils("FluxKontext")
     fe = make_front_end(u)
+    for name, plans in make_family_schedules(u).items():
+        print(name, ["".join("S" if st["skip"] else "C" for st in p["steps"]) for p in plans])
     print("front end:", {k: len(v) if hasattr(v, "__len__") else v for k, v in fe.items()})
     cases = make_region_ops(u)
     for c in cases:

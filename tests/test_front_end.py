@@ -92,3 +92,29 @@ def test_patched_scheduler_keeps_an_inspectable_signature():
     assert {"sigmas", "mu", "timesteps"} <= set(inspect.signature(s.set_timesteps).parameters)
     schedule.retrieve_timesteps(s, 28, "cpu", sigmas=np.linspace(1.0, 1 / 28, 28), mu=1.15)
     assert s.sigmas.shape[0] == 29
+
+
+def test_avdc_plans_of_every_family_match_their_own_loop_code(golden_dir):
+    """tests/golden/family_schedules.json: each family's AVDC block + gamma table exec'd from its inplace.py
+    (oracle/make_golden.make_family_schedules). The product's host planner and the oracle's must take the same
+    compute / skip decisions and reuse ratios, bit for bit, for all five pipelines."""
+    from oracle.schedule import avdc_plan, flow_match_sigmas
+    from regione_b200.manager import RegionManager, plan_steps
+    with open(os.path.join(golden_dir, "family_schedules.json")) as f:
+        golden = json.load(f)
+    assert set(golden) == set(params.GAMMA)
+    _, ts = flow_match_sigmas(28, 4096)
+    for name, plans in golden.items():
+        assert len(plans) == 3
+        for p in plans:
+            m = RegionManager()
+            m.set_parameters(p["params"])
+            plan = plan_steps(ts, params.GAMMA[name], m)
+            assert [bool(s) for s, _ in plan] == [st["skip"] for st in p["steps"]], (name, p["params"])
+            for (skip, ratio), st in zip(plan, p["steps"]):
+                if skip:
+                    assert float(ratio) == st["ratio"], (name, p["params"])
+            prm = p["params"]
+            o = avdc_plan(ts, params.GAMMA[name], warmup_step=prm["warmup_step"], post_step=prm["post_step"],
+                          refresh_step=prm["refresh_step"], cache_threshold=prm["cache_threshold"])
+            assert [s["mode"] == "SKIP" for s in o] == [st["skip"] for st in p["steps"]], (name, p["params"])
