@@ -273,9 +273,39 @@ def make_family_schedules(u):
     return out
 
 
+def make_cfg():
+    """Classifier-free-guidance arithmetic of the CFG families, produced by the reference's own lines on seeded bf16
+    velocities: Step1XEdit/inplace.py:401-410 (norm-processed, above and below `timesteps_truncate`; `process_diff_norm`
+    is the fork's function, absent here -> the stand-in the product tests use, passed in as `self`) and
+    QwenImageEdit/inplace.py:401-405 (norm rescaling)."""
+    from regione_b200.standin_step1x import Step1XEditPipeline
+    g = torch.Generator().manual_seed(5)
+    pos = torch.randn(1, 512, 64, generator=g).bfloat16()
+    neg = (pos.float() + 0.5 * torch.randn(1, 512, 64, generator=g)).bfloat16()
+    step1x_src = ref_lines(f"{REF}/Step1XEdit/inplace.py", 401, 410)
+    qwen_src = ref_lines(f"{REF}/QwenImageEdit/inplace.py", 401, 405)
+    out = dict(pos=pos, neg=neg, step1x=[], qwen=[])
+
+    class _Self:
+        process_diff_norm = staticmethod(Step1XEditPipeline.process_diff_norm)
+    for t, scale in ((torch.tensor(976.2), 6.0), (torch.tensor(904.5), 6.0), (torch.tensor(935.6), 4.0)):
+        env = dict(torch=torch, noise_pred=pos.clone(), neg_noise_pred=neg.clone(), t=t, timesteps_truncate=930.0,
+                   true_cfg_scale=scale, process_norm_power=0.4, self=_Self())
+        exec(step1x_src, env)
+        out["step1x"].append(dict(t=float(t), truncate=930.0, scale=scale, k=0.4, out=env["noise_pred"].clone()))
+    for scale in (4.0, 1.5):
+        env = dict(torch=torch, noise_pred=pos.clone(), neg_noise_pred=neg.clone(), true_cfg_scale=scale)
+        exec(qwen_src, env)
+        out["qwen"].append(dict(scale=scale, out=env["noise_pred"].clone()))
+    torch.save(out, os.path.join(OUT, "cfg.pt"))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     u = load_reference_utils("FluxKontext")
+    cfg = make_cfg()
+    print("cfg:", len(cfg["step1x"]), "step1x cases,", len(cfg["qwen"]), "qwen cases")
     fe = make_front_end(u)
     for name, plans in make_family_schedules(u).items():
         print(name, ["".join("S" if st["skip"] else "C" for st in p["steps"]) for p in plans])

@@ -118,6 +118,15 @@ class QwenOracle:
         return torch.exp(e / half)
 
 
+def cfg_norm_rescaled(pos, neg, true_cfg_scale):
+    """Qwen-Image classifier-free guidance with norm rescaling, RegionE/QwenImageEdit/inplace.py:401-405 (same in
+    QwenImageEditPlus). Pinned by tests/golden/cfg.pt (the reference's own lines exec'd)."""
+    comb = neg + true_cfg_scale * (pos - neg)
+    cond_norm = torch.norm(pos, dim=-1, keepdim=True)
+    noise_norm = torch.norm(comb, dim=-1, keepdim=True)
+    return comb * (cond_norm / noise_norm)
+
+
 def run_regione_qwen(model: QwenOracle, params: dict, latents, image_latents, prompt_embeds, negative_prompt_embeds,
                      true_cfg_scale, img_freqs, txt_freqs, neg_txt_freqs, height, width, record=False):
     """QwenImageEdit/inplace.py:322-433 for output_type='latent'."""
@@ -163,10 +172,7 @@ def run_regione_qwen(model: QwenOracle, params: dict, latents, image_latents, pr
             if do_cfg:                                                                     # :386-405
                 neg = model.forward(st, x_in, negative_prompt_embeds, timestep / 1000, img_freqs, neg_txt_freqs,
                                     latent_ids, "uncond")[:, : latents.size(1)]
-                comb = neg + true_cfg_scale * (noise_pred - neg)
-                cond_norm = torch.norm(noise_pred, dim=-1, keepdim=True)
-                noise_norm = torch.norm(comb, dim=-1, keepdim=True)
-                noise_pred = comb * (cond_norm / noise_norm)
+                noise_pred = cfg_norm_rescaled(noise_pred, neg, true_cfg_scale)
             cache = noise_pred
             trace["modes"].append("FULL" if full else "REGION")
         latents = scheduler_step(sch, st, noise_pred, latents, trace)

@@ -45,6 +45,17 @@ class Step1XOracle(FluxOracle):
         return self.lin("proj_out", h)                                                     # :566-567
 
 
+def cfg_norm_processed(pos, neg, true_cfg_scale, t, timesteps_truncate, process_diff_norm, process_norm_power):
+    """Step1X classifier-free guidance, RegionE/Step1XEdit/inplace.py:401-410 (same in Step1XEditV1P2): above the
+    truncation timestep the guidance term is divided by the fork's `process_diff_norm` of the per-token norm of
+    (pos - neg). Pinned by tests/golden/cfg.pt (the reference's own lines exec'd)."""
+    if t.item() > timesteps_truncate:
+        diff = pos - neg
+        diff_norm = torch.norm(diff, dim=(2), keepdim=True)
+        return neg + true_cfg_scale * (pos - neg) / process_diff_norm(diff_norm, k=process_norm_power)
+    return neg + true_cfg_scale * (pos - neg)
+
+
 def run_regione_step1x(model, params, latents, image_latents, latent_ids, text_ids, prompt_embeds, prompt_mask,
                        negative_prompt_embeds, negative_mask, true_cfg_scale, process_diff_norm, height, width,
                        timesteps_truncate=0.93, process_norm_power=0.4, record=False):
@@ -95,13 +106,8 @@ def run_regione_step1x(model, params, latents, image_latents, latent_ids, text_i
             pred = pred[:, : latents.size(1)]
             if do_cfg:
                 noise_pred, neg = pred.chunk(2)
-                if t.item() > timesteps_truncate:                                          # :401-407
-                    diff = noise_pred - neg
-                    diff_norm = torch.norm(diff, dim=(2), keepdim=True)
-                    noise_pred = neg + true_cfg_scale * (noise_pred - neg) / process_diff_norm(diff_norm,
-                                                                                               k=process_norm_power)
-                else:
-                    noise_pred = neg + true_cfg_scale * (noise_pred - neg)
+                noise_pred = cfg_norm_processed(noise_pred, neg, true_cfg_scale, t, timesteps_truncate,
+                                                process_diff_norm, process_norm_power)
             else:
                 noise_pred = pred
             cache = noise_pred
@@ -184,11 +190,8 @@ def run_regione_step1x_v1p2(model, params, gamma, latents, image_latents, latent
             timestep = t.expand(latents.shape[0]).to(latents.dtype)
             pos = model.forward_tag(st, x_in, pe, timestep / 1000, latent_ids, "cond")[:, : latents.size(1)]
             neg = model.forward_tag(st, x_in, ne, timestep / 1000, latent_ids, "uncond")[:, : latents.size(1)]
-            if t.item() > timesteps_truncate:
-                diff_norm = torch.norm(pos - neg, dim=(2), keepdim=True)
-                noise_pred = neg + true_cfg_scale * (pos - neg) / process_diff_norm(diff_norm, k=process_norm_power)
-            else:
-                noise_pred = neg + true_cfg_scale * (pos - neg)
+            noise_pred = cfg_norm_processed(pos, neg, true_cfg_scale, t, timesteps_truncate, process_diff_norm,
+                                            process_norm_power)
             cache = noise_pred
             trace["modes"].append("FULL" if full else "REGION")
         latents = scheduler_step(sch, st, noise_pred, latents, trace)
