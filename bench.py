@@ -217,7 +217,8 @@ def run_ours(args):
     region_steps = modes.count("REGION")
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:            # one nvidia-smi poller per box is enough (8 of them at 5 Hz perturb the host)
+        sampler.start()
     lib.rge_profile_enable(1)
     launches0 = lib.rge_launch_count()
     if args.profiler_range:           # ncu --profile-from-start off: capture exactly the timed images
@@ -230,7 +231,7 @@ def run_ours(args):
     lib.rge_profile_collect(pms, psum, pwork, pcnt)
     lib.rge_profile_enable(0)
     ms_e2e = timed(image_e2e, args.steps)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
     value = world * args.steps / (ms / 1e3)
     e2e_value = world * args.steps / (ms_e2e / 1e3)
