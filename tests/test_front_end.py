@@ -118,3 +118,20 @@ def test_avdc_plans_of_every_family_match_their_own_loop_code(golden_dir):
             o = avdc_plan(ts, params.GAMMA[name], warmup_step=prm["warmup_step"], post_step=prm["post_step"],
                           refresh_step=prm["refresh_step"], cache_threshold=prm["cache_threshold"])
             assert [s["mode"] == "SKIP" for s in o] == [st["skip"] for st in p["steps"]], (name, p["params"])
+
+
+def test_cli_sharding_and_rho_sweep(monkeypatch):
+    items = list(range(10))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert cli._shard(items) == items
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    got = []
+    for r in range(4):
+        monkeypatch.setenv("RANK", str(r))
+        part = cli._shard(items)
+        assert part == items[r::4]
+        got += part
+    assert sorted(got) == items                                   # every item exactly once, no collective involved
+    a = cli.build_parser("Step1X-Edit-v1p2").parse_args(["--rho", "sweep"])
+    assert {cli._rho(a, s) for s in range(50)} == set(cli.RHO_SWEEP)
+    assert cli._rho(cli.build_parser("FluxKontext").parse_args(["--rho", "0.4"]), 3) == 0.4
