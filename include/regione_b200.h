@@ -207,7 +207,10 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
  *   v_out [n_out, in_channels]   velocity of the first n_out active tokens (the noise tokens; inplace.py:347)
  * K/V rows of the active tokens (and of all text tokens) are written into the persistent cache of every layer,
  * attention runs active-Q x full cache. A FULL step therefore (re)writes the whole cache, which subsumes the
- * reference's "write cache at warmup-1 / refresh" modes (inplace.py:717-725). */
+ * reference's "write cache at warmup-1 / refresh" modes (inplace.py:717-725).
+ * Stream semantics: independent launches of a block fork onto library-owned side streams (one of them high priority)
+ * and join back into `stream` before the call returns to the host, so for the caller the call is asynchronous on
+ * `stream` like every other entry point; two handles must not run concurrently on one device. */
 int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
                  float timestep_x1000, void* v_out, int32_t n_out, void* stream);
 
