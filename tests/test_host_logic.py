@@ -134,3 +134,19 @@ def test_c_abi_library_loads_and_exports_declared_symbols():
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     # argument validation happens before any CUDA call
     assert lib.rge_op_gemm(None, None) == -1 and b"null" in lib.rge_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under regione_b200/ (host modules, CLI, C sources) may import, call
+    or mention it, and the product has no CPU fallback to route through."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "regione_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|\boracle\.", re.M)
+    checked = 0
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(text), f"{f} refers to the oracle package"
+                checked += 1
+    assert checked > 20
