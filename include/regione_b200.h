@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RGE_ABI_VERSION 3
+#define RGE_ABI_VERSION 4
 
 enum rge_status {
   RGE_OK = 0,
@@ -32,6 +32,10 @@ enum rge_status {
 
 int rge_abi_version(void);
 const char* rge_last_error(void);
+/* Run-time tuning knob of the kernels (same names as the RGE_* environment variables they start from, lower case
+ * without the prefix: "attn_poly", "attn_split", "gemm_bn", "2cta_min_m", "raster"). For benchmarks that sweep
+ * variants inside one process; results never depend on them beyond the stated tolerances. */
+int rge_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Kernel-level entry points (each replaces one reference op; also what the parity tests call)
@@ -54,7 +58,15 @@ typedef struct rge_gemm_desc {
   const void* gate; const void* res; int64_t ldr;            /* RGE_EPI_GATE_RES: out = res + gate[n]*(..) */
   const void* norm_w; const float* rope_cs;                   /* RGE_EPI_NORM_ROPE: RMSNorm weight[128], table */
   const int32_t* rope_map; int32_t rope_off;                  /*   rope row = (rope_map?rope_map[m]:m)+rope_off */
+  int64_t rope_ld;                                            /*   0: rope_cs is [S][64][2]; > 0: pair-major
+                                                                   [64][rope_ld][2] (coalesced per epilogue warp) */
+  int32_t flags;                                              /* RGE_GEMM_* bits */
 } rge_gemm_desc;
+/* RGE_EPI_STORE only: round fp32 -> fp16 -> bf16 like the reference's Triton kernel does before its store
+ * (`accumulator.to(tl.float16)`, fused_kernels.py:80) instead of fp32 -> bf16. For differential tests
+ * against that kernel; the engine stores fp32 -> bf16 directly. bias, gate, norm_w, out and res must be 16-byte
+ * aligned. */
+#define RGE_GEMM_FP16_ROUNDTRIP 1
 int rge_op_gemm(const rge_gemm_desc* d, void* stream);
 /* n (1..6) independent GEMMs as ONE persistent launch: the q / k / v (/ MLP-up) projections of a block, or the image-
  * and text-stream halves of one stage of a double block. Results are identical to n rge_op_gemm calls; members with
@@ -200,7 +212,10 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
                     const void* pooled, float guidance_x1000, void* stream);
 
 /* One transformer forward on the active image tokens.
- *   x_in  [n_img, in_channels]   packed latents of the active image tokens (noise first, then condition tokens)
+ *   x_in   [n_x, in_channels]    packed latents of the active noise tokens
+ *   x_cond [n_cond, in_channels] packed instruction-image (condition) tokens that follow them, or NULL / 0: FULL steps
+ *                                pass the condition latent here instead of concatenating it behind the noise latent
+ *                                (inplace.py:332); n_img = n_x + n_cond active image tokens in total
  *   sel   int32 [n_img] or NULL  position of each active token in the full [L+C] image sequence; NULL = identity
  *                                (FULL step, n_img must be L+C); REGION step: the edited ids (inplace.py:727-732)
  *   timestep_x1000               the bf16-rounded timestep the reference feeds time_text_embed
@@ -211,8 +226,8 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
  * Stream semantics: independent launches of a block fork onto library-owned side streams (one of them high priority)
  * and join back into `stream` before the call returns to the host, so for the caller the call is asynchronous on
  * `stream` like every other entry point; two handles must not run concurrently on one device. */
-int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
-                 float timestep_x1000, void* v_out, int32_t n_out, void* stream);
+int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_x, const void* x_cond, int32_t n_cond,
+                 const int32_t* sel, float timestep_x1000, void* v_out, int32_t n_out, void* stream);
 
 /* Variants for families whose front end is not FLUX's (rge_config.external_embed = 1).
  *   rope_cs       fp32 [T+L+C, 64, 2] (cos, sin) per rotary pair for the FULL key sequence, text rows first — what
@@ -226,8 +241,9 @@ int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, c
  * Call before rge_begin_image[_ex] of that pass. */
 int rge_set_pass_text_len(rge_handle* h, int32_t pass, int32_t txt_len);
 int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const void* ctx_embedded, void* stream);
-int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
-                    const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out, void* stream);
+int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_x, const void* x_cond, int32_t n_cond,
+                    const int32_t* sel, const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out,
+                    void* stream);
 
 /* Optional timing of the engine's tensor-core launches with CUDA events on the streams they run on (bench.py
  * roofline). rge_profile_collect synchronises the device and returns, per class c (0 = GEMM, 1 = attention):

@@ -100,7 +100,7 @@ class QwenOracle:
         t = timestep.to(h.dtype)                                                           # :517
         enc = self.lin("txt_in", rms_norm(encoder_hidden_states, self.w["txt_norm.weight"]))   # :518-519
         # diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0, scale=1000): angle = (t * f) * 1000
-        ang = 1000 * (t[:, None].float() * self._freq()[None, :])
+        ang = 1000 * (t[:, None].float() * self._freq().to(t.device)[None, :])
         tp = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
         temb = self.lin("time_text_embed.timestep_embedder.linear_2",
                         F.silu(self.lin("time_text_embed.timestep_embedder.linear_1", tp.to(h.dtype))))   # :524-528
@@ -134,9 +134,11 @@ def run_regione_qwen(model: QwenOracle, params: dict, latents, image_latents, pr
     st.set_parameters(params)
     n_steps = params["num_inference_steps"]
     sigmas, timesteps = flow_match_sigmas(n_steps, latents.shape[1])
+    g = torch.tensor(params.get("gamma") or GAMMA_QWEN, dtype=torch.float16, device=latents.device)
+    assert g.numel() == n_steps - 1
+    sigmas, timesteps = sigmas.to(latents.device), timesteps.to(latents.device)
     sch = EulerState(sigmas, timesteps)
-    g = torch.tensor(GAMMA_QWEN, dtype=torch.float16)
-    latent_ids = torch.arange(latents.shape[1] + image_latents.shape[1])                  # :322
+    latent_ids = torch.arange(latents.shape[1] + image_latents.shape[1], device=latents.device)   # :322
     st.refresh(latents, image_latents, latent_ids, torch.empty(prompt_embeds.shape[1], 0), height, width)
     cache, accumulate = None, 1
     do_cfg = negative_prompt_embeds is not None

@@ -15,6 +15,8 @@ c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_floa
 
 RGE_OK = 0
 EPI_STORE, EPI_GELU, EPI_GATE_RES, EPI_NORM_ROPE = 0, 1, 2, 3
+GEMM_FP16_ROUNDTRIP = 1
+ABI_VERSION = 4
 BLK_GLOBAL, BLK_DOUBLE, BLK_SINGLE = 0, 1, 2
 
 GLOBAL_SLOTS = [
@@ -56,6 +58,7 @@ class GemmDesc(C.Structure):
         ("gate", c_void_p), ("res", c_void_p), ("ldr", c_int64),
         ("norm_w", c_void_p), ("rope_cs", c_void_p),
         ("rope_map", c_void_p), ("rope_off", c_int32),
+        ("rope_ld", c_int64), ("flags", c_int32),
     ]
 
 
@@ -81,6 +84,7 @@ PROTOTYPES = {
     "rge_abi_version": (c_int32, []),
     "rge_last_error": (C.c_char_p, []),
     "rge_launch_count": (c_int64, []),
+    "rge_set_option": (c_int32, [C.c_char_p, c_int32]),
     "rge_profile_enable": (c_int32, [c_int32]),
     "rge_profile_collect": (c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(c_int64)]),
@@ -111,10 +115,10 @@ PROTOTYPES = {
     "rge_begin_image": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "rge_set_pass_text_len": (c_int32, [c_void_p, c_int32, c_int32]),
     "rge_begin_image_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
-    "rge_dit_step_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_int32, c_void_p]),
-    "rge_dit_step": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_float, c_void_p, c_int32,
-                               c_void_p]),
+    "rge_dit_step_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_void_p]),
+    "rge_dit_step": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_float, c_void_p,
+                               c_int32, c_void_p]),
 }
 
 
@@ -132,10 +136,12 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
-    if not os.path.exists(path):
-        try:
-            _build.build_library()
-        except Exception as e:  # noqa: BLE001
+    # build_library() is a no-op when the library is newer than every source (mtime check) and compiles under a file
+    # lock, so concurrent ranks do not write the same objects; without nvcc a prebuilt library is used as is
+    try:
+        _build.build_library()
+    except Exception as e:  # noqa: BLE001
+        if not os.path.exists(path):
             raise RegionEB200Error(
                 f"regione_b200: CUDA library {path} is missing and could not be built ({e}); "
                 "run `python -m regione_b200.build` — there is no CPU fallback") from e
@@ -144,8 +150,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rge_abi_version() != 3:
-        raise RegionEB200Error("regione_b200: ABI version mismatch")
+    if lib.rge_abi_version() != ABI_VERSION:
+        raise RegionEB200Error(f"regione_b200: ABI version mismatch (library {lib.rge_abi_version()}, binding "
+                               f"{ABI_VERSION}): rebuild with `python -m regione_b200.build --force`")
     _LIB = lib
     return lib
 

@@ -39,10 +39,24 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if stale) and return the path of the shared library."""
+    """Compile (if stale) and return the path of the shared library. Serialised across processes by a file lock
+    (ranks of one torchrun job start together)."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "regione_b200.h"))
+    sources = [os.path.join(CSRC, f) for f in SOURCES]
+    if not force and os.path.exists(LIB_PATH) and not _stale(LIB_PATH, sources + headers):
+        return LIB_PATH          # fresh: nothing to do (also the path taken on a box without nvcc)
     nvcc = _nvcc()
     objs = []
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "tuning.cuh"
 
 using namespace rge;
 typedef __nv_bfloat16 bf16;
@@ -28,11 +30,15 @@ enum { PC_GEMM = 0, PC_ATTN = 1, PC_NCLS = 2 };
 struct ProfRec { int cls; double work; cudaEvent_t a, b; int m, n, k; };
 bool g_prof = false;
 cudaEvent_t g_base = nullptr;
+std::mutex g_prof_mu;              // the records / event pool may be touched from several host threads
 std::vector<ProfRec> g_recs;
 std::vector<cudaEvent_t> g_pool;
 cudaEvent_t prof_event() {
   cudaEvent_t e;
-  if (!g_pool.empty()) { e = g_pool.back(); g_pool.pop_back(); return e; }
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_pool.empty()) { e = g_pool.back(); g_pool.pop_back(); return e; }
+  }
   cudaEventCreate(&e);
   return e;
 }
@@ -46,6 +52,7 @@ struct ProfScope {
     if (a) {
       cudaEvent_t b = prof_event();
       cudaEventRecord(b, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
       g_recs.push_back(ProfRec{cls, work, a, b, m, n, k});
     }
   }
@@ -72,14 +79,13 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 int device_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[kMaxDevices] = {};   // per device
+  const int dev = current_device();
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 GemmArgs to_args(const rge_gemm_desc* d) {
@@ -94,6 +100,7 @@ GemmArgs to_args(const rge_gemm_desc* d) {
   a.gate = (const bf16*)d->gate; a.res = (const bf16*)d->res; a.ldr = d->ldr;
   a.norm_w = (const bf16*)d->norm_w; a.rope_cs = (const float2*)d->rope_cs;
   a.rope_map = d->rope_map; a.rope_off = d->rope_off;
+  a.rope_ld = d->rope_ld; a.flags = d->flags;
   return a;
 }
 
@@ -102,6 +109,11 @@ GemmArgs to_args(const rge_gemm_desc* d) {
 extern "C" {
 
 int rge_abi_version(void) { return RGE_ABI_VERSION; }
+
+int rge_set_option(const char* name, int32_t value) {
+  if (!name || !set_tuning(name, value)) return fail(RGE_ERR_INVALID, "rge_set_option: unknown option '%s'", name ? name : "");
+  return RGE_OK;
+}
 const char* rge_last_error(void) { return g_err; }
 int64_t rge_launch_count(void) { return g_launches.load(); }
 
@@ -119,6 +131,7 @@ int rge_profile_enable(int32_t on) {
 int rge_profile_collect(double* ms_busy, double* ms_sum, double* work, int64_t* count) {
   if (!ms_busy || !ms_sum || !work || !count) return fail(RGE_ERR_INVALID, "rge_profile_collect: null argument");
   RGE_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   std::vector<std::pair<float, float>> iv[PC_NCLS];
   for (int c = 0; c < PC_NCLS; ++c) { ms_busy[c] = 0; ms_sum[c] = 0; work[c] = 0; count[c] = 0; }
   // RGE_PROFILE_DUMP=<file>: append one line per launch (class, stream-ready ms, end ms, M/Sq, N/Skv, K/H) - the
@@ -233,7 +246,7 @@ int rge_cfg_combine(const void* pos, const void* neg, float scale, const void* d
 
 int rge_op_rope_table(const float* ids, float* cs, int32_t S, void* stream) {
   if (!ids || !cs) return fail(RGE_ERR_INVALID, "rge_op_rope_table: null operand");
-  RGE_LAUNCH(launch_rope_table(ids, (float2*)cs, S, (cudaStream_t)stream));
+  RGE_LAUNCH(launch_rope_table(ids, (float2*)cs, S, 0, (cudaStream_t)stream));
   return RGE_OK;
 }
 
@@ -307,7 +320,7 @@ struct rge_handle {
   bf16 *mods = nullptr, *small = nullptr;  // small: tproj[256] t1[D] t2[D] temb[D]
   bf16 *ctx = nullptr;                     // [n_pass][T, D]
   bf16 *pass_small = nullptr;              // per pass: gproj[256] g1[D] gemb[D] pooled[pooled_dim] p1[D] pemb[D]
-  float2* rope = nullptr;                  // [n_pass][S, 64]
+  float2* rope = nullptr;                  // [n_pass][64][S] pair-major (cos, sin): row s of pair p at p * S + s
   float* ids = nullptr;                    // [S, 3] staging
   int *sel_img = nullptr, *sel_all = nullptr;
   GemvJob* jobs = nullptr;                 // [2 + n_mod] step jobs, then per pass 4 image jobs
@@ -369,12 +382,12 @@ int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, 
 GemmArgs mk(const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bias, int N, int epi, bf16* out, long ldo,
             const int* row_map, int row_off, int col_off, const bf16* gate = nullptr, const bf16* res = nullptr,
             long ldr = 0, const bf16* norm_w = nullptr, const float2* rope = nullptr, const int* rope_map = nullptr,
-            int rope_off = 0) {
+            int rope_off = 0, long rope_ld = 0) {
   GemmArgs a;
   a.A = A; a.lda = lda; a.M = M; a.K = K; a.W = W; a.ldw = K; a.N = N; a.bias = bias; a.epilogue = epi;
   a.out = out; a.ldo = ldo; a.row_map = row_map; a.row_off = row_off; a.col_off = col_off;
   a.gate = gate; a.res = res; a.ldr = ldr; a.norm_w = norm_w; a.rope_cs = rope; a.rope_map = rope_map;
-  a.rope_off = rope_off;
+  a.rope_off = rope_off; a.rope_ld = rope_ld;
   return a;
 }
 
@@ -447,11 +460,11 @@ struct StepRun {
   // ---- the GEMMs of a double block (b) / single block (b); k / v rows are scattered into the cache at T + sel[m]
   GemmArgs img_q(int b) const {
     return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_Q_W), h->Dw(b, RGE_D_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, T, 0,
-              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T);
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_Q), rope, h->sel_img, T, h->S);
   }
   GemmArgs img_k(int b, bf16* kc) const {
     return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_K_W), h->Dw(b, RGE_D_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_img, T, 0,
-              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T);
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_K), rope, h->sel_img, T, h->S);
   }
   GemmArgs img_v(int b, bf16* vc) const {
     return mk(n_img_p, D, M, D, h->Dw(b, RGE_D_V_W), h->Dw(b, RGE_D_V_B), D, EPI_STORE, vc, D, h->sel_img, T, 0);
@@ -459,11 +472,11 @@ struct StepRun {
   // text stream q / k / v: recomputed every step (the reference does not cache text K/V)
   GemmArgs txt_q(int b) const {
     return mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_Q_W), h->Dw(b, RGE_D_ADD_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0,
-              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0);
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_Q), rope, nullptr, 0, h->S);
   }
   GemmArgs txt_k(int b, bf16* kc) const {
     return mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_K_W), h->Dw(b, RGE_D_ADD_K_B), D, EPI_NORM_ROPE, kc, D, nullptr, 0, 0,
-              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0);
+              nullptr, nullptr, 0, h->Dw(b, RGE_D_NORM_ADD_K), rope, nullptr, 0, h->S);
   }
   GemmArgs txt_v(int b, bf16* vc) const {
     return mk(h->n, D, T, D, h->Dw(b, RGE_D_ADD_V_W), h->Dw(b, RGE_D_ADD_V_B), D, EPI_STORE, vc, D, nullptr, 0, 0);
@@ -495,11 +508,11 @@ struct StepRun {
   // single block on [text; image]; selection = [0..T) ++ (T + sel) (inplace.py:730)
   GemmArgs s_q(int b) const {
     return mk(h->n, D, MA, D, h->Sw(b, RGE_S_Q_W), h->Sw(b, RGE_S_Q_B), D, EPI_NORM_ROPE, h->q, D, nullptr, 0, 0, nullptr,
-              nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0);
+              nullptr, 0, h->Sw(b, RGE_S_NORM_Q), rope, h->sel_all, 0, h->S);
   }
   GemmArgs s_k(int b, bf16* kc) const {
     return mk(h->n, D, MA, D, h->Sw(b, RGE_S_K_W), h->Sw(b, RGE_S_K_B), D, EPI_NORM_ROPE, kc, D, h->sel_all, 0, 0, nullptr,
-              nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0);
+              nullptr, 0, h->Sw(b, RGE_S_NORM_K), rope, h->sel_all, 0, h->S);
   }
   GemmArgs s_v(int b, bf16* vc) const {
     return mk(h->n, D, MA, D, h->Sw(b, RGE_S_V_W), h->Sw(b, RGE_S_V_B), D, EPI_STORE, vc, D, h->sel_all, 0, 0);
@@ -856,7 +869,7 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
   if (T > 0) RGE_CUDA(cudaMemcpyAsync(h->ids, txt_ids, (size_t)T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RGE_CUDA(cudaMemcpyAsync(h->ids + (size_t)T * 3, img_ids, (size_t)(h->L + h->C) * 3 * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
-  RGE_LAUNCH(launch_rope_table(h->ids, h->rope + (size_t)pass * h->S * 64, T + h->L + h->C, st));
+  RGE_LAUNCH(launch_rope_table(h->ids, h->rope + (size_t)pass * h->S * 64, T + h->L + h->C, h->S, st));
   // context_embedder (inplace.py:480): same value every step of the image, so computed once
   RGE_TRY(gemm(h, st, (const bf16*)enc, h->cfg.ctx_dim, T, h->cfg.ctx_dim, h->G(RGE_G_CTX_EMBED_W),
                h->G(RGE_G_CTX_EMBED_B), D, EPI_STORE, h->ctx + (size_t)pass * h->T * D, D, nullptr, 0, 0));
@@ -872,13 +885,16 @@ int rge_begin_image(rge_handle* h, int32_t pass, const float* txt_ids, const flo
   return RGE_OK;
 }
 
-static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
-                         float timestep_x1000, const void* ext_temb, const void* ext_ctx, void* v_out, int32_t n_out,
-                         void* stream) {
-  if (!h || (n_out > 0 && !v_out) || (n_img > 0 && !x_in)) return fail(RGE_ERR_INVALID, "rge_dit_step: null argument");
+static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t n_x, const void* x_cond, int32_t n_cond,
+                         const int32_t* sel, float timestep_x1000, const void* ext_temb, const void* ext_ctx,
+                         void* v_out, int32_t n_out, void* stream) {
+  if (!h || (n_out > 0 && !v_out) || (n_x > 0 && !x_in) || (n_cond > 0 && !x_cond))
+    return fail(RGE_ERR_INVALID, "rge_dit_step: null argument");
   if (pass < 0 || pass >= h->cfg.n_pass) return fail(RGE_ERR_INVALID, "rge_dit_step: bad pass %d", pass);
   if (!h->finalized || !h->begun[pass]) return fail(RGE_ERR_STATE, "rge_dit_step: rge_begin_image not called");
-  if (n_img < 0 || n_img > h->L + h->C || (!sel && n_img != h->L + h->C))
+  if (n_x < 0 || n_cond < 0) return fail(RGE_ERR_INVALID, "rge_dit_step: negative row count");
+  const int n_img = n_x + n_cond;   // active image tokens: the rows of x_in, then the rows of x_cond
+  if (n_img > h->L + h->C || (!sel && n_img != h->L + h->C))
     return fail(RGE_ERR_INVALID, "rge_dit_step: n_img %d invalid (sel %s, L+C %d)", n_img, sel ? "set" : "null",
                 h->L + h->C);
   if (n_out < 0 || n_out > n_img) return fail(RGE_ERR_INVALID, "rge_dit_step: n_out %d > n_img %d", n_out, n_img);
@@ -912,8 +928,12 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   if (T > 0)
     RGE_CUDA(cudaMemcpyAsync(h->h, ext_ctx ? (const bf16*)ext_ctx : h->ctx + (size_t)pass * h->T * D,
                              (size_t)T * D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
-  RGE_TRY(gemm(h, st, (const bf16*)x_in, h->cfg.in_channels, M, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
+  // x_embedder over the two row ranges (the reference concatenates latents and image_latents first, inplace.py:332;
+  // reading them through two pointers spares that copy)
+  RGE_TRY(gemm(h, st, (const bf16*)x_in, h->cfg.in_channels, n_x, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
                h->G(RGE_G_X_EMBED_B), D, EPI_STORE, h->h, D, nullptr, T, 0));
+  RGE_TRY(gemm(h, st, (const bf16*)x_cond, h->cfg.in_channels, n_cond, h->cfg.in_channels, h->G(RGE_G_X_EMBED_W),
+               h->G(RGE_G_X_EMBED_B), D, EPI_STORE, h->h, D, nullptr, T + n_x, 0));
 
   StepRun r(h, st, pass, T, M);
   const bf16* mod = h->mods;
@@ -937,16 +957,18 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   return RGE_OK;
 }
 
-int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
-                 float timestep_x1000, void* v_out, int32_t n_out, void* stream) {
+int rge_dit_step(rge_handle* h, int32_t pass, const void* x_in, int32_t n_x, const void* x_cond, int32_t n_cond,
+                 const int32_t* sel, float timestep_x1000, void* v_out, int32_t n_out, void* stream) {
   if (h && (h->cfg.external_embed & 2)) return fail(RGE_ERR_STATE, "rge_dit_step: handle uses rge_dit_step_ex");
-  return dit_step_impl(h, pass, x_in, n_img, sel, timestep_x1000, nullptr, nullptr, v_out, n_out, stream);
+  return dit_step_impl(h, pass, x_in, n_x, x_cond, n_cond, sel, timestep_x1000, nullptr, nullptr, v_out, n_out,
+                       stream);
 }
 
-int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_img, const int32_t* sel,
-                    const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out, void* stream) {
+int rge_dit_step_ex(rge_handle* h, int32_t pass, const void* x_in, int32_t n_x, const void* x_cond, int32_t n_cond,
+                    const int32_t* sel, const void* temb, const void* ctx_embedded, void* v_out, int32_t n_out,
+                    void* stream) {
   if (!temb) return fail(RGE_ERR_INVALID, "rge_dit_step_ex: null temb");
-  return dit_step_impl(h, pass, x_in, n_img, sel, 0.f, temb, ctx_embedded, v_out, n_out, stream);
+  return dit_step_impl(h, pass, x_in, n_x, x_cond, n_cond, sel, 0.f, temb, ctx_embedded, v_out, n_out, stream);
 }
 
 int rge_set_pass_text_len(rge_handle* h, int32_t pass, int32_t txt_len) {
@@ -968,8 +990,9 @@ int rge_begin_image_ex(rge_handle* h, int32_t pass, const float* rope_cs, const 
     return fail(RGE_ERR_UNSUPPORTED, "rge_begin_image_ex: guidance / pooled embeddings need an external temb");
   cudaStream_t st = (cudaStream_t)stream;
   const int Tp = h->Tp[pass];
-  RGE_CUDA(cudaMemcpyAsync(h->rope + (size_t)pass * h->S * 64, rope_cs,
-                           (size_t)(Tp + h->L + h->C) * 64 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  // kept pair-major ([64][S]) inside the library: the 32 rows of an epilogue warp then read each pair coalesced
+  RGE_LAUNCH(launch_rope_transpose((const float2*)rope_cs, h->rope + (size_t)pass * h->S * 64, Tp + h->L + h->C, h->S,
+                                   st));
   if (ctx_embedded && Tp > 0)
     RGE_CUDA(cudaMemcpyAsync(h->ctx + (size_t)pass * h->T * h->D, ctx_embedded,
                              (size_t)Tp * h->D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));

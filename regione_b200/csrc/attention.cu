@@ -19,6 +19,7 @@
 #include "attention.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "tuning.cuh"
 
 namespace rge {
 
@@ -30,6 +31,7 @@ constexpr int kHalfBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled half
 constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kSlots = 5;
 constexpr int kSmemBytes = 2 * kTileBytes + kSlots * kTileBytes + 256 + 1024;
+constexpr int kDefaultPoly = 0;         // exponential pairs of every 8 on the FMA pipe (RGE_ATTN_POLY overrides)
 constexpr uint32_t kColS = 0, kColO = 256;  // TMEM column bases: S_i at kColS + 128 i, O_i at kColO + 128 i
 
 struct AttnDev {
@@ -45,20 +47,38 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], relative error 7.5e-5,
-// far below the bf16 rounding of P): used for one score in four so that the MUFU pipe, which is co-critical with the
-// tensor pipe in this kernel (16 ex2 per clock per SM), is not the only source of exponentials.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float r = x + 12582912.0f;                 // 1.5 * 2^23: round-to-nearest integer lands in the low mantissa bits
-  const float f = x - (r - 12582912.0f);           // fraction in [-0.5, 0.5]
-  float p = fmaf(0.055171459913253784f, f, 0.2426108568906784f);
-  p = fmaf(p, f, 0.6932609677314758f);
-  p = fmaf(p, f, 0.9999281167984009f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+// 2^x for a PAIR of arguments on the FMA / ALU pipes: clamp, Cody-Waite split with the round-to-nearest magic constant,
+// degree-3 minimax polynomial on [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding of P) evaluated with
+// packed FFMA2, exponent re-inserted with one shift-add per element. The MUFU pipe (16 ex2 per clock per SM) needs
+// exactly as long for a 128 x 128 score tile as the tensor pipe needs for its two MMAs, so every exponential moved here
+// shortens the softmax leg of the ping-pong below the MMA leg.
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2f(x, x0, x1);
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  const uint64_t xc = pack2f(x0, x1);
+  const uint64_t magic = pack2f(12582912.0f, 12582912.0f);   // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const uint64_t r = add2(xc, magic);
+  const uint64_t f = sub2(xc, sub2(r, magic));               // fraction in [-0.5, 0.5]
+  uint64_t p = fma2(pack2f(0.055171459913253784f, 0.055171459913253784f), f,
+                    pack2f(0.2426108568906784f, 0.2426108568906784f));
+  p = fma2(p, f, pack2f(0.6932609677314758f, 0.6932609677314758f));
+  p = fma2(p, f, pack2f(0.9999281167984009f, 0.9999281167984009f));
+  float r0, r1, q0, q1;
+  unpack2f(r, r0, r1);
+  unpack2f(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
 
-// kPoly = how many of every four exponentials use ex2_poly instead of MUFU.EX2 (0, 1 or 2).
+// which of the 8 pairs of a 16-score group take the polynomial path, for kPoly = 0, 2, 3, 4 pairs of 8
+__device__ __forceinline__ constexpr bool poly_pair(int kPoly, int pair) {
+  return kPoly == 4 ? (pair & 1) : kPoly == 3 ? (pair == 2 || pair == 5 || pair == 7)
+       : kPoly == 2 ? (pair == 3 || pair == 7) : false;
+}
+
+// kPoly = how many of every eight score PAIRS use ex2_poly2 instead of MUFU.EX2 (0, 2, 3 or 4).
 template <int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -226,11 +246,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       // row maximum of the raw scores, four independent chains
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int jj = 0; jj < 128; jj += 8) {
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[jj + 0]), __uint_as_float(v[jj + 1])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3])));
-        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[jj + 4]), __uint_as_float(v[jj + 5])));
-        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[jj + 6]), __uint_as_float(v[jj + 7])));
+      for (int jj = 0; jj < 128; jj += 8) {   // FMNMX3: one instruction per two scores
+        mx0 = max3f(mx0, __uint_as_float(v[jj + 0]), __uint_as_float(v[jj + 1]));
+        mx1 = max3f(mx1, __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+        mx2 = max3f(mx2, __uint_as_float(v[jj + 4]), __uint_as_float(v[jj + 5]));
+        mx3 = max3f(mx3, __uint_as_float(v[jj + 6]), __uint_as_float(v[jj + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       if (j == 0) {
@@ -257,20 +277,35 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           m_run = m_new;
         }
       }
-      // pass 2: P = exp2((s - m) * scale * log2 e), packed bf16 pairs into the first 64 columns of S_i
+      // pass 2: P = exp2((s - m) * scale * log2 e), packed bf16 pairs into the first 64 columns of S_i. Scale-and-shift
+      // and the row sum run as packed FFMA2 / FADD2 (one issue slot per two scores).
+      const uint64_t sl2_2 = pack2f(sl2, sl2);
       const float neg_m = -m_run * sl2;
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      const uint64_t neg_m2 = pack2f(neg_m, neg_m);
+      uint64_t sum_a = pack2f(0.f, 0.f), sum_b = sum_a;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
 #pragma unroll
         for (int jj = 64 * half; jj < 64 * half + 64; jj += 4) {
-          const float p0 = ex2(fmaf(__uint_as_float(v[jj + 0]), sl2, neg_m));
-          const float p1 = ex2(fmaf(__uint_as_float(v[jj + 1]), sl2, neg_m));
-          const float a2 = fmaf(__uint_as_float(v[jj + 2]), sl2, neg_m);
-          const float a3 = fmaf(__uint_as_float(v[jj + 3]), sl2, neg_m);
-          const float p2 = kPoly >= 2 ? ex2_poly(a2) : ex2(a2);
-          const float p3 = kPoly >= 1 ? ex2_poly(a3) : ex2(a3);
-          sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+          const uint64_t xa = fma2(pack2u(v[jj + 0], v[jj + 1]), sl2_2, neg_m2);
+          const uint64_t xb = fma2(pack2u(v[jj + 2], v[jj + 3]), sl2_2, neg_m2);
+          float p0, p1, p2, p3;
+          if (poly_pair(kPoly, (jj >> 1) & 7)) {
+            ex2_poly2(xa, p0, p1);
+          } else {
+            unpack2f(xa, p0, p1);
+            p0 = ex2(p0);
+            p1 = ex2(p1);
+          }
+          if (poly_pair(kPoly, ((jj >> 1) + 1) & 7)) {
+            ex2_poly2(xb, p2, p3);
+          } else {
+            unpack2f(xb, p2, p3);
+            p2 = ex2(p2);
+            p3 = ex2(p3);
+          }
+          sum_a = add2(sum_a, pack2f(p0, p1));
+          sum_b = add2(sum_b, pack2f(p2, p3));
           v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
           v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
         }
@@ -281,6 +316,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_half[2 * grp + half]);
       }
+      float sum0, sum1, sum2, sum3;
+      unpack2f(sum_a, sum0, sum1);
+      unpack2f(sum_b, sum2, sum3);
       l_run += (sum0 + sum1) + (sum2 + sum3);
     }
     // epilogue: O_i / l -> bf16 -> global
@@ -319,17 +357,22 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
   if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
-  static int poly = -1;
-  if (poly < 0) {
-    const char* env = getenv("RGE_ATTN_POLY");   // tuning knob: 0 (default, fastest measured), 1 or 2 of every 4 exponentials on the FMA pipe
-    poly = env ? atoi(env) : 0;
-    if (poly < 0 || poly > 2) poly = 0;
+  // tuning knob attn_poly / RGE_ATTN_POLY: 0, 2, 3 or 4 of every 8 exponential pairs on the FMA pipe instead of MUFU
+  int poly = tuning().attn_poly;
+  if (poly < 0) poly = kDefaultPoly;
+  if (poly != 2 && poly != 3 && poly != 4) poly = 0;
+  const int dev = current_device();
+  static bool attr_set[kMaxDevices] = {};   // per device: a process may drive several GPUs
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
   }
   CUtensorMap mq, mk, mv;
   if (!make_tmap_bf16_2d(&mq, a.Q, a.Sq, (uint64_t)a.H * 128, a.ldq, kTile)) return cudaErrorInvalidValue;
@@ -344,7 +387,8 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
   if (poly == 0) attention_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   else if (poly == 2) attention_kernel<2><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
-  else attention_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  else if (poly == 3) attention_kernel<3><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  else attention_kernel<4><<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
 

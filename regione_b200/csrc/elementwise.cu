@@ -3,6 +3,7 @@
 // Reference behaviour restated per kernel; see oracle/ for the CPU restatement the tests compare against.
 #include "elementwise.cuh"
 #include "ptx.cuh"
+#include "tuning.cuh"
 
 namespace rge {
 
@@ -281,17 +282,29 @@ __global__ void add3_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, cons
 }
 
 // ------------------------------------------------------------------ rotary table (FluxPosEmbed)
-__global__ void rope_table_kernel(const float* __restrict__ ids, float2* __restrict__ cs, int S) {
+// ld == 0: cs is [S][64] row-major; ld > 0: pair-major [64][ld] (what the GEMM epilogue reads coalesced per warp)
+__global__ void rope_table_kernel(const float* __restrict__ ids, float2* __restrict__ cs, int S, long ld) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * 64) return;
-  const int s = idx >> 6, p = idx & 63;
+  const int s = ld > 0 ? idx % S : idx >> 6, p = ld > 0 ? idx / S : idx & 63;
   int axis, j, dim;
   if (p < 8) { axis = 0; j = p; dim = 16; }
   else if (p < 36) { axis = 1; j = p - 8; dim = 56; }
   else { axis = 2; j = p - 36; dim = 56; }
   const double freq = 1.0 / pow(10000.0, (double)(2 * j) / (double)dim);
   const double ang = (double)ids[s * 3 + axis] * freq;
-  cs[idx] = make_float2((float)cos(ang), (float)sin(ang));
+  cs[ld > 0 ? (long)p * ld + s : (long)idx] = make_float2((float)cos(ang), (float)sin(ang));
+}
+
+// [S][64] row-major -> pair-major [64][ld] through a 32 x 32 shared-memory tile
+__global__ void rope_transpose_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int S, long ld) {
+  __shared__ float2 tile[32][33];
+  const int s0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    if (s0 + r < S) tile[r][threadIdx.x] = src[(long)(s0 + r) * 64 + p0 + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    if (s0 + threadIdx.x < S) dst[(long)(p0 + r) * ld + s0 + threadIdx.x] = tile[threadIdx.x][r];
 }
 
 __global__ void build_selection_kernel(const int* sel_img, int n_img, int T, int* sel_img_out, int* sel_all_out) {
@@ -678,9 +691,15 @@ cudaError_t launch_add3(const __nv_bfloat16* a, const __nv_bfloat16* b, const __
   return cudaGetLastError();
 }
 
-cudaError_t launch_rope_table(const float* ids, float2* cs, int S, cudaStream_t s) {
+cudaError_t launch_rope_table(const float* ids, float2* cs, int S, long ld, cudaStream_t s) {
   if (S <= 0) return cudaSuccess;
-  rope_table_kernel<<<cdiv((long)S * 64, 256), 256, 0, s>>>(ids, cs, S);
+  rope_table_kernel<<<cdiv((long)S * 64, 256), 256, 0, s>>>(ids, cs, S, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rope_transpose(const float2* src, float2* dst, int S, long ld, cudaStream_t s) {
+  if (S <= 0) return cudaSuccess;
+  rope_transpose_kernel<<<dim3(cdiv(S, 32), 2), dim3(32, 8), 0, s>>>(src, dst, S, ld);
   return cudaGetLastError();
 }
 
@@ -745,11 +764,12 @@ cudaError_t launch_morph_compact(const uint8_t* mask_in, uint8_t* mask_out, int 
                                  int* edited, int* unedited, int* counts, cudaStream_t s) {
   const int L = gh * gw;
   if (L <= 0 || 2 * L > 96 * 1024) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // per device
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(morph_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   morph_compact_kernel<<<1, 1024, 2 * L, s>>>(mask_in, mask_out, gh, gw, erosion_dilation, edited, unedited, counts);
   return cudaGetLastError();

@@ -41,8 +41,11 @@ cudaError_t launch_timestep_proj(float t, __nv_bfloat16* out256, cudaStream_t s)
 cudaError_t launch_add3(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c, __nv_bfloat16* out,
                         int n, cudaStream_t s);
 
-// Rotary table: ids [S,3] fp32 -> cs [S,64] (cos, sin), axes (16,56,56), theta 10000, fp64 angles.
-cudaError_t launch_rope_table(const float* ids, float2* cs, int S, cudaStream_t s);
+// Rotary table: ids [S,3] fp32 -> (cos, sin) per rotary pair, axes (16,56,56), theta 10000, fp64 angles.
+// ld == 0: cs is [S][64] row-major; ld > 0: pair-major [64][ld] (the GEMM epilogue's coalesced layout).
+cudaError_t launch_rope_table(const float* ids, float2* cs, int S, long ld, cudaStream_t s);
+// [S][64] row-major table -> pair-major [64][ld]
+cudaError_t launch_rope_transpose(const float2* src, float2* dst, int S, long ld, cudaStream_t s);
 
 // sel_all = [0..T-1, T + sel_img[i]]; sel_img == null means identity over n_img.
 cudaError_t launch_build_selection(const int* sel_img, int n_img, int T, int* sel_img_out, int* sel_all_out,

@@ -317,11 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_group_kernel(const __grid_co
 // The fixed cost (in output columns) stands for the prologue / epilogue drain of a tile and for the A-tile re-reads of
 // narrow tiles; ties go to the wider tile. RGE_GEMM_BN=<n> forces a width (tuning / tests).
 int pick_bn(const GemmArgs& a, int num_sms) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* env = getenv("RGE_GEMM_BN");
-    forced = env ? atoi(env) : 0;
-  }
+  const int forced = tuning().gemm_bn;
   const bool heads = a.epilogue == EPI_NORM_ROPE;
   if (forced > 0 && forced <= kMaxBN && forced % (heads ? 128 : 32) == 0) return forced;
   const int num_m = (a.M + BM - 1) / BM;
@@ -343,11 +339,12 @@ int pick_bn(const GemmArgs& a, int num_sms) {
 
 template <int EPI>
 cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};   // per device: the attribute belongs to the device's copy of the function
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   TileCfg cfg;
   cfg.bn = pick_bn(a, num_sms);
@@ -374,11 +371,16 @@ cudaError_t launch_1cta(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 bool gemm_args_ok(const GemmArgs& a) {
   if (a.K <= 0 || (a.K % 8) || (a.N % 32) || (a.lda % 8) || (a.ldw % 8) || (a.ldo % 8) || (a.col_off % 8)) return false;
   if (a.epilogue < EPI_STORE || a.epilogue > EPI_NORM_ROPE) return false;
-  if (a.epilogue == EPI_NORM_ROPE && ((a.N % 128) || !a.norm_w || !a.rope_cs)) return false;
-  if (a.epilogue == EPI_GATE_RES && (!a.gate || !a.res || (a.ldr % 8))) return false;
+  if (a.epilogue == EPI_NORM_ROPE && ((a.N % 128) || !a.norm_w || !a.rope_cs || !aligned16(a.norm_w))) return false;
+  if (a.epilogue == EPI_GATE_RES && (!a.gate || !a.res || (a.ldr % 8) || !aligned16(a.gate) || !aligned16(a.res)))
+    return false;
+  // per-column vectors are read 16 bytes at a time in the epilogue; rows of out / res start 16-byte aligned
+  if (!aligned16(a.bias) || !aligned16(a.out)) return false;
   return a.A && a.W && a.out;
 }
 
@@ -394,11 +396,12 @@ cudaError_t launch_gemm_group(const GemmArgs* args, int n, int num_sms, cudaStre
   }
   if (n_live == 0) return cudaSuccess;
   if (n_live == 1) return launch_gemm(*live[0], num_sms, stream);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   // one width cap for the whole group: every member takes its widest allowed tile <= cap; the cap minimises
   //   (sum of tile costs) / SMs  +  half the longest tile   with tile cost = (bn + 32) * K
@@ -461,16 +464,9 @@ void* get_tensor_map_encoder() { return reinterpret_cast<void*>(tensor_map_encod
 
 cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return cudaSuccess;  // empty edited set: nothing to do
-  if (a.K <= 0 || (a.K % 8) || (a.N % 32) || (a.lda % 8) || (a.ldw % 8) || (a.ldo % 8) || (a.col_off % 8))
-    return cudaErrorInvalidValue;
-  if (a.epilogue == EPI_NORM_ROPE && (a.N % 128)) return cudaErrorInvalidValue;
-  if (a.epilogue == EPI_GATE_RES && (!a.gate || !a.res || (a.ldr % 8))) return cudaErrorInvalidValue;
+  if (!gemm_args_ok(a)) return cudaErrorInvalidValue;
   // large-M launches (FULL steps) go to the CTA-pair kernel; RGE_2CTA_MIN_M=0 disables it
-  static int min_m_2cta = -1;
-  if (min_m_2cta < 0) {
-    const char* env = getenv("RGE_2CTA_MIN_M");
-    min_m_2cta = env ? atoi(env) : 2048;
-  }
+  const int min_m_2cta = tuning().min_m_2cta;
   if (min_m_2cta > 0 && a.M >= min_m_2cta && a.N % 256 == 0) {
     cudaError_t e = launch_gemm_2cta(a, num_sms, stream);
     if (e != cudaErrorNotSupported) return e;

@@ -36,6 +36,8 @@ struct GemmArgs {
   const float2* rope_cs = nullptr;        // [S, 64] (cos, sin) per rotary pair
   const int* rope_map = nullptr;          // rope row = (rope_map ? rope_map[m] : m) + rope_off
   int rope_off = 0;
+  long rope_ld = 0;                       // 0: rope_cs is [S][64]; > 0: pair-major [64][rope_ld] (coalesced per warp)
+  int flags = 0;                          // bit 0: EPI_STORE stores through fp16 (fused_kernels.py:80)
 };
 
 // Launches on `stream`; returns cudaSuccess or the launch/encode error. `num_sms` bounds the persistent grid.

@@ -3,7 +3,9 @@
 #pragma once
 #include <cstdlib>
 #include "gemm.cuh"
+#include <cuda_fp16.h>
 #include "ptx.cuh"
+#include "tuning.cuh"
 
 namespace rge {
 
@@ -21,6 +23,8 @@ struct GemmDev {
   const float2* rope_cs;
   const int* rope_map;
   int rope_off;
+  long rope_ld;   // 0: rope_cs is [S][64] row-major; > 0: pair-major [64][rope_ld]
+  int flags;      // bit 0: EPI_STORE rounds fp32 -> fp16 -> bf16 (the reference's Triton kernel, fused_kernels.py:80)
   int n_fast;   // tile order: 0 = consecutive tiles walk down M (W tile shared, A streamed), 1 = walk along N
 };
 
@@ -31,11 +35,7 @@ struct GemmDev {
 // 0.33 GB). Those launches walk along N instead: A is read once band by band and W (75 - 94 MB) is the operand that
 // lives in L2. RGE_RASTER=m|n forces one order (tuning).
 inline int pick_n_fast(const GemmArgs& a) {
-  static int forced = -2;
-  if (forced == -2) {
-    const char* env = getenv("RGE_RASTER");
-    forced = !env ? -1 : (env[0] == 'n' ? 1 : (env[0] == 'm' ? 0 : -1));
-  }
+  const int forced = tuning().raster;
   if (forced >= 0) return forced;
   const double a_bytes = 2.0 * a.M * a.K, w_bytes = 2.0 * a.N * a.K;
   return a_bytes > 96e6 && w_bytes < a_bytes ? 1 : 0;
@@ -47,11 +47,81 @@ inline GemmDev to_dev(const GemmArgs& a) {
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.row_map = a.row_map; p.row_off = a.row_off; p.col_off = a.col_off;
   p.gate = a.gate; p.res = a.res; p.ldr = a.ldr;
   p.norm_w = a.norm_w; p.rope_cs = a.rope_cs; p.rope_map = a.rope_map; p.rope_off = a.rope_off;
+  p.rope_ld = a.rope_ld; p.flags = a.flags;
   p.n_fast = 0;
   return p;
 }
 
-__device__ __forceinline__ float ldg_bf16f(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+// Eight consecutive bf16 of a per-column vector (bias, gate, RMSNorm weight) as floats: one 16-byte read-only load,
+// same address in every lane (broadcast), instead of eight scalar loads. Pointers are 16-byte aligned (checked on the
+// host), column offsets are multiples of 8.
+__device__ __forceinline__ void ld_vec8(const __nv_bfloat16* ptr, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(ptr));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// fp32 -> fp16 -> fp32: the rounding the reference's Triton scatter-GEMM applies before its store into the bf16 cache
+// (`accumulator.to(tl.float16)`, RegionE/FluxKontext/fused_kernels.py:80); only with RGE_GEMM_FP16_ROUNDTRIP.
+__device__ __forceinline__ float fp16_roundtrip(float x) { return __half2float(__float2half_rn(x)); }
+
+// One 32-column chunk of the STORE / GELU / GATE_RES epilogues: v = accumulator columns [n0, n0 + 32) of this thread's
+// row, rv = the residual row's same columns (GATE_RES only).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&v)[32], const uint4 (&rv)[4],
+                                               __nv_bfloat16* out_ptr, int n0, bool valid) {
+  uint32_t o[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float b[8], gt[8];
+    if (p.bias) ld_vec8(p.bias + n0 + 8 * g, b);
+    if constexpr (EPI == EPI_GATE_RES) ld_vec8(p.gate + n0 + 8 * g, gt);
+    const uint32_t rw[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
+      float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
+      if constexpr (EPI == EPI_STORE) {
+        if (p.flags & 1) { x0 = fp16_roundtrip(x0); x1 = fp16_roundtrip(x1); }
+      } else {
+        bf16_round2(x0, x1);
+      }
+      if constexpr (EPI == EPI_GELU) {
+        x0 = gelu_tanh(x0);
+        x1 = gelu_tanh(x1);
+      } else if constexpr (EPI == EPI_GATE_RES) {
+        float g0 = gt[j] * x0, g1 = gt[j + 1] * x1;
+        bf16_round2(g0, g1);
+        x0 = __uint_as_float(rw[j >> 1] << 16) + g0;
+        x1 = __uint_as_float(rw[j >> 1] & 0xffff0000u) + g1;
+      }
+      o[4 * g + (j >> 1)] = pack_bf16x2(x0, x1);
+    }
+  }
+  if (valid) {
+    uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void load_residual(const GemmDev& p, uint4 (&rv)[4], int m, int n0, bool valid) {
+  if constexpr (EPI == EPI_GATE_RES) {
+    if (valid) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long)m * p.ldr + n0);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) rv[t] = rp[t];
+      return;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) rv[t] = make_uint4(0, 0, 0, 0);
+}
 
 // taddr: TMEM address of this thread's row (lane field set) at column 0 of the accumulator; m: global row;
 // n_base: first global column of the tile; bn: tile width (multiple of 32; of 128 for EPI_NORM_ROPE). All 32 lanes of
@@ -63,42 +133,68 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
   __nv_bfloat16* out_ptr = p.out + out_row * p.ldo + p.col_off;
   if constexpr (EPI == EPI_NORM_ROPE) {
     const long rope_row = valid ? (long)((p.rope_map ? __ldg(p.rope_map + m) : m) + p.rope_off) : 0;
-    const float2* cs_row = p.rope_cs + rope_row * 64;
+    // rotary table: [S][64] (cos, sin) row-major, or - p.rope_ld > 0 - pair-major [64][rope_ld]: consecutive rows of
+    // one pair are then consecutive in memory, so the 32 rows of a warp read 256 contiguous bytes per pair instead of
+    // 32 separate sectors
+    const float2* cs_base = p.rope_ld > 0 ? p.rope_cs + rope_row : p.rope_cs + rope_row * 64;
+    const long cs_step = p.rope_ld > 0 ? p.rope_ld : 1;
 #pragma unroll 1
     for (int h = 0; h < bn / 128; ++h) {
       const int n0 = n_base + h * 128;
       if (n0 >= p.N) break;
-      float ss = 0.f;
+      // pass 1: sum of squares of the bf16-rounded (acc + bias) over the head, two 32-column TMEM loads in flight
+      float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + h * 128 + c * 32, v);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t v[64];
+        tmem_ld32p(taddr + h * 128 + c * 32, v);
+        tmem_ld32p(taddr + h * 128 + c * 32 + 32, v + 32);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float b = p.bias ? ldg_bf16f(p.bias + n0 + c * 32 + j) : 0.f;
-          float x = bf16_round(__uint_as_float(v[j]) + b);
-          ss += x * x;
+        for (int g = 0; g < 8; ++g) {
+          float b[8];
+          if (p.bias) ld_vec8(p.bias + n0 + c * 32 + 8 * g, b);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
+            float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
+            bf16_round2(x0, x1);
+            ss0 = fmaf(x0, x0, ss0);
+            ss1 = fmaf(x1, x1, ss1);
+          }
         }
       }
-      const float rstd = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+      const float rstd = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + 1e-6f);
+      // pass 2: normalise, weight, rotate, store; the rotary pairs of chunk c are requested before its TMEM load
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + h * 128 + c * 32, v);
+        float2 cs[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          cs[j] = valid ? __ldg(cs_base + (long)(c * 16 + j) * cs_step) : make_float2(1.f, 0.f);
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int d = c * 32 + j;
-          float b0 = p.bias ? ldg_bf16f(p.bias + n0 + d) : 0.f;
-          float b1 = p.bias ? ldg_bf16f(p.bias + n0 + d + 1) : 0.f;
-          float x0 = bf16_round(__uint_as_float(v[j]) + b0);
-          float x1 = bf16_round(__uint_as_float(v[j + 1]) + b1);
-          x0 = bf16_round(bf16_round(x0 * rstd) * ldg_bf16f(p.norm_w + d));
-          x1 = bf16_round(bf16_round(x1 * rstd) * ldg_bf16f(p.norm_w + d + 1));
-          float2 cs = valid ? __ldg(cs_row + (d >> 1)) : make_float2(1.f, 0.f);
-          o[j >> 1] = pack_bf16x2(x0 * cs.x - x1 * cs.y, x1 * cs.x + x0 * cs.y);
+        for (int g = 0; g < 4; ++g) {
+          float b[8], w[8];
+          if (p.bias) ld_vec8(p.bias + n0 + c * 32 + 8 * g, b);
+          ld_vec8(p.norm_w + c * 32 + 8 * g, w);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
+            float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
+            bf16_round2(x0, x1);
+            x0 *= rstd;
+            x1 *= rstd;
+            bf16_round2(x0, x1);
+            x0 *= w[j];
+            x1 *= w[j + 1];
+            bf16_round2(x0, x1);
+            const float2 t = cs[4 * g + (j >> 1)];
+            o[4 * g + (j >> 1)] = pack_bf16x2(x0 * t.x - x1 * t.y, x1 * t.x + x0 * t.y);
+          }
         }
         if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0 + c * 32);
@@ -108,46 +204,30 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
       }
     }
   } else {
+    // software pipeline over 32-column chunks: the TMEM load (and, for GATE_RES, the residual-row loads, whose L2 /
+    // DRAM latency one thread per row cannot hide otherwise) of chunk c + 1 are in flight while chunk c is processed
+    int n_chunks = (p.N - n_base) / 32;
+    if (n_chunks > bn / 32) n_chunks = bn / 32;
+    if (n_chunks <= 0) return;
+    uint32_t va[32], vb[32];
+    uint4 ra[4], rb[4];
+    tmem_ld32(taddr, va);
+    load_residual<EPI>(p, ra, m, n_base, valid);
 #pragma unroll 1
-    for (int c = 0; c < bn / 32; ++c) {
-      const int n0 = n_base + c * 32;
-      if (n0 >= p.N) break;
-      uint32_t v[32];
-      tmem_ld32(taddr + c * 32, v);
+    for (int c = 0; c < n_chunks; c += 2) {
       tmem_ld_wait();
-      uint32_t o[16];
-      uint4 rv[4];
-      if constexpr (EPI == EPI_GATE_RES) {
-        if (valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long)m * p.ldr + n0);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) rv[t] = rp[t];
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) rv[t] = make_uint4(0, 0, 0, 0);
-        }
+      if (c + 1 < n_chunks) {
+        tmem_ld32(taddr + (c + 1) * 32, vb);
+        load_residual<EPI>(p, rb, m, n_base + (c + 1) * 32, valid);
       }
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float b0 = p.bias ? ldg_bf16f(p.bias + n0 + j) : 0.f;
-        float b1 = p.bias ? ldg_bf16f(p.bias + n0 + j + 1) : 0.f;
-        float x0 = bf16_round(__uint_as_float(v[j]) + b0);
-        float x1 = bf16_round(__uint_as_float(v[j + 1]) + b1);
-        if constexpr (EPI == EPI_GELU) {
-          x0 = gelu_tanh(x0);
-          x1 = gelu_tanh(x1);
-        } else if constexpr (EPI == EPI_GATE_RES) {
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-          __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(&rw[j >> 1]);
-          x0 = __bfloat162float(rr.x) + bf16_round(ldg_bf16f(p.gate + n0 + j) * x0);
-          x1 = __bfloat162float(rr.y) + bf16_round(ldg_bf16f(p.gate + n0 + j + 1) * x1);
+      epilogue_chunk<EPI>(p, va, ra, out_ptr, n_base + c * 32, valid);
+      if (c + 1 < n_chunks) {
+        tmem_ld_wait();
+        if (c + 2 < n_chunks) {
+          tmem_ld32(taddr + (c + 2) * 32, va);
+          load_residual<EPI>(p, ra, m, n_base + (c + 2) * 32, valid);
         }
-        o[j >> 1] = pack_bf16x2(x0, x1);
-      }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+        epilogue_chunk<EPI>(p, vb, rb, out_ptr, n_base + (c + 1) * 32, valid);
       }
     }
   }

@@ -1,0 +1,58 @@
+// Process-wide tuning knobs of the kernels. Each knob starts from its environment variable (read once) and can be
+// changed at run time through rge_set_option (include/regione_b200.h) so that a benchmark can sweep variants inside one
+// process. Defaults are the fastest measured settings (profiles/).
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+
+namespace rge {
+
+// Function attributes (dynamic shared memory size) are per device: launchers remember them per device index.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+
+struct Tuning {
+  int attn_poly;     // RGE_ATTN_POLY:   exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
+  int attn_split;    // RGE_ATTN_SPLIT:  KV splits of the attention grid, 0 = choose per launch
+  int gemm_bn;       // RGE_GEMM_BN:     forced tile width of the 1-CTA GEMM, 0 = choose per launch
+  int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never
+  int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
+};
+
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? atoi(e) : dflt;
+}
+
+inline Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning x;
+    x.attn_poly = env_int("RGE_ATTN_POLY", -1);
+    x.attn_split = env_int("RGE_ATTN_SPLIT", 0);
+    x.gemm_bn = env_int("RGE_GEMM_BN", 0);
+    x.min_m_2cta = env_int("RGE_2CTA_MIN_M", 2048);
+    const char* r = getenv("RGE_RASTER");
+    x.raster = !r ? -1 : (r[0] == 'n' ? 1 : (r[0] == 'm' ? 0 : -1));
+    return x;
+  }();
+  return t;
+}
+
+// returns false for an unknown knob
+inline bool set_tuning(const char* name, int value) {
+  Tuning& t = tuning();
+  if (!strcmp(name, "attn_poly")) t.attn_poly = value;
+  else if (!strcmp(name, "attn_split")) t.attn_split = value;
+  else if (!strcmp(name, "gemm_bn")) t.gemm_bn = value;
+  else if (!strcmp(name, "2cta_min_m")) t.min_m_2cta = value;
+  else if (!strcmp(name, "raster")) t.raster = value;
+  else return false;
+  return true;
+}
+
+}  // namespace rge

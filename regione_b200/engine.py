@@ -47,6 +47,7 @@ class FluxEngine:
         self.key = (txt_len, lat_len, cond_len, n_pass)
         self.in_channels = in_ch
         self._keep = []  # borrowed by the library: keep the tensors alive as long as the handle
+        self._src = []   # (module, attribute, data_ptr, shape) of every registered weight, for weights_current()
         self._h = C.c_void_p()
         check(self.lib.rge_create(C.byref(cfg), C.byref(self._h)), "rge_create")
         try:
@@ -57,14 +58,27 @@ class FluxEngine:
             raise
 
     # ------------------------------------------------------------------ weights
-    def _set(self, kind, index, slot, tensor, name):
+    def _set(self, kind, index, slot, tensor, name, owner=None, attr=None):
         t = _w(tensor, name)
         self._keep.append(t)
+        if owner is not None:
+            self.__dict__.setdefault("_src", []).append((owner, attr, t.data_ptr(), tuple(t.shape)))
         check(self.lib.rge_set_weight(self._h, kind, index, slot, ptr(t)), f"rge_set_weight({name})")
 
     def _lin(self, kind, index, table, stem, mod, name):
-        self._set(kind, index, table[stem + "_W"], mod.weight, name + ".weight")
-        self._set(kind, index, table[stem + "_B"], mod.bias, name + ".bias")
+        self._set(kind, index, table[stem + "_W"], mod.weight, name + ".weight", mod, "weight")
+        self._set(kind, index, table[stem + "_B"], mod.bias, name + ".bias", mod, "bias")
+
+    def weights_current(self) -> bool:
+        """The handle BORROWS raw weight pointers (the reference reads the live module weights on every call). True
+        iff every registered parameter still lives where it was registered, with the same shape, in bf16 on the GPU;
+        `pipeline.to(...)`, LoRA fusing, `load_state_dict(assign=True)` or CPU offload re-allocate parameters and make
+        this False, upon which the caller rebuilds the engine (`_get_engine`) instead of running on stale memory."""
+        for owner, attr, p, shape in self.__dict__.get("_src", ()):
+            t = getattr(owner, attr, None)
+            if t is None or t.data_ptr() != p or tuple(t.shape) != shape or t.dtype != torch.bfloat16 or not t.is_cuda:
+                return False
+        return True
 
     def _register(self, tr, blocks, singles):
         g, d, s = _lib.BLK_GLOBAL, _lib.BLK_DOUBLE, _lib.BLK_SINGLE
@@ -96,10 +110,12 @@ class FluxEngine:
             self._lin(d, i, DS, "ADD_Q", a.add_q_proj, n + "attn.add_q_proj")
             self._lin(d, i, DS, "ADD_K", a.add_k_proj, n + "attn.add_k_proj")
             self._lin(d, i, DS, "ADD_V", a.add_v_proj, n + "attn.add_v_proj")
-            self._set(d, i, DS["NORM_Q"], a.norm_q.weight, n + "attn.norm_q.weight")
-            self._set(d, i, DS["NORM_K"], a.norm_k.weight, n + "attn.norm_k.weight")
-            self._set(d, i, DS["NORM_ADD_Q"], a.norm_added_q.weight, n + "attn.norm_added_q.weight")
-            self._set(d, i, DS["NORM_ADD_K"], a.norm_added_k.weight, n + "attn.norm_added_k.weight")
+            self._set(d, i, DS["NORM_Q"], a.norm_q.weight, n + "attn.norm_q.weight", a.norm_q, "weight")
+            self._set(d, i, DS["NORM_K"], a.norm_k.weight, n + "attn.norm_k.weight", a.norm_k, "weight")
+            self._set(d, i, DS["NORM_ADD_Q"], a.norm_added_q.weight, n + "attn.norm_added_q.weight", a.norm_added_q,
+                      "weight")
+            self._set(d, i, DS["NORM_ADD_K"], a.norm_added_k.weight, n + "attn.norm_added_k.weight", a.norm_added_k,
+                      "weight")
             self._lin(d, i, DS, "OUT", a.to_out[0], n + "attn.to_out.0")
             self._lin(d, i, DS, "ADD_OUT", a.to_add_out, n + "attn.to_add_out")
             self._lin(d, i, DS, "FF_UP", b.ff.net[0].proj, n + "ff.net.0.proj")
@@ -113,8 +129,8 @@ class FluxEngine:
             self._lin(s, i, SS, "Q", a.to_q, n + "attn.to_q")
             self._lin(s, i, SS, "K", a.to_k, n + "attn.to_k")
             self._lin(s, i, SS, "V", a.to_v, n + "attn.to_v")
-            self._set(s, i, SS["NORM_Q"], a.norm_q.weight, n + "attn.norm_q.weight")
-            self._set(s, i, SS["NORM_K"], a.norm_k.weight, n + "attn.norm_k.weight")
+            self._set(s, i, SS["NORM_Q"], a.norm_q.weight, n + "attn.norm_q.weight", a.norm_q, "weight")
+            self._set(s, i, SS["NORM_K"], a.norm_k.weight, n + "attn.norm_k.weight", a.norm_k, "weight")
             self._lin(s, i, SS, "MLP", b.proj_mlp, n + "proj_mlp")
             self._lin(s, i, SS, "OUT", b.proj_out, n + "proj_out")
 
@@ -132,18 +148,27 @@ class FluxEngine:
         check(self.lib.rge_begin_image(self._h, pass_id, ptr(ti), ptr(ii), ptr(pe), ptr(po), float(guidance_x1000),
                                        stream_ptr()), "rge_begin_image")
 
-    def step(self, x_in, sel, timestep_x1000: float, n_out: int, pass_id: int = 0, out=None):
-        """x_in [n_img, C] bf16; sel int32 [n_img] or None (identity over L+C); returns velocity [n_out, C]."""
-        x = x_in.contiguous()
+    @staticmethod
+    def _rows(x, what):
+        if x is None:
+            return None, 0
+        x = x.contiguous()
         if x.dtype != torch.bfloat16 or not x.is_cuda:
-            raise _lib.RegionEB200Error("latents must be bf16 CUDA tensors")
+            raise _lib.RegionEB200Error(f"{what} must be bf16 CUDA tensors")
+        return x, x.shape[0]
+
+    def step(self, x_in, sel, timestep_x1000: float, n_out: int, pass_id: int = 0, out=None, x_cond=None):
+        """x_in [n_x, C] bf16 (+ x_cond [n_cond, C]: the condition rows that follow, read in place instead of a
+        concatenated copy); sel int32 [n_x + n_cond] or None (identity over L+C); returns velocity [n_out, C]."""
+        x, n_x = self._rows(x_in, "latents")
+        xc, n_c = self._rows(x_cond, "condition latents")
         if out is None:
             out = torch.empty(n_out, self.in_channels, dtype=torch.bfloat16, device=x.device)
         sel_ptr = ptr(sel)
         if sel is not None and sel.numel() == 0:   # empty edited set: NULL would mean "identity"
             sel_ptr = ptr(self._dummy_sel(x.device))
-        check(self.lib.rge_dit_step(self._h, pass_id, ptr(x) if x.numel() else None, x.shape[0], sel_ptr,
-                                    float(timestep_x1000), ptr(out) if n_out else None, n_out, stream_ptr()),
+        check(self.lib.rge_dit_step(self._h, pass_id, ptr(x) if n_x else None, n_x, ptr(xc) if n_c else None, n_c,
+                                    sel_ptr, float(timestep_x1000), ptr(out) if n_out else None, n_out, stream_ptr()),
               "rge_dit_step")
         return out
 
@@ -164,3 +189,19 @@ class FluxEngine:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+def cached_engine(transformer, key, factory):
+    """One resident engine (KV cache) per transformer, keyed on the sequence shape. Rebuilt when the shape changes or
+    when any borrowed weight pointer went stale (`weights_current`); the stale handle is destroyed first."""
+    cache = transformer.__dict__.setdefault("_regione_b200_engines", {})
+    eng = cache.get(key)
+    if eng is not None and not eng.weights_current():
+        eng = None
+    if eng is None:
+        for old in list(cache.values()):   # shapes rarely change: never hold two KV caches
+            old.close()
+        cache.clear()
+        eng = factory()
+        cache[key] = eng
+    return eng

@@ -35,6 +35,7 @@ class QwenEngine(FluxEngine):
         self.in_channels = in_ch
         self.transformer = tr
         self._keep = []
+        self._src = []
         self._h = C.c_void_p()
         check(self.lib.rge_create(C.byref(cfg), C.byref(self._h)), "rge_create")
         try:
@@ -63,10 +64,10 @@ class QwenEngine(FluxEngine):
             self._lin(d, i, DS, "ADD_Q", a.add_q_proj, n + "attn.add_q_proj")
             self._lin(d, i, DS, "ADD_K", a.add_k_proj, n + "attn.add_k_proj")
             self._lin(d, i, DS, "ADD_V", a.add_v_proj, n + "attn.add_v_proj")
-            self._set(d, i, DS["NORM_Q"], a.norm_q.weight, n + "attn.norm_q.weight")
-            self._set(d, i, DS["NORM_K"], a.norm_k.weight, n + "attn.norm_k.weight")
-            self._set(d, i, DS["NORM_ADD_Q"], a.norm_added_q.weight, n + "attn.norm_added_q.weight")
-            self._set(d, i, DS["NORM_ADD_K"], a.norm_added_k.weight, n + "attn.norm_added_k.weight")
+            self._set(d, i, DS["NORM_Q"], a.norm_q.weight, n + "attn.norm_q.weight", a.norm_q, "weight")
+            self._set(d, i, DS["NORM_K"], a.norm_k.weight, n + "attn.norm_k.weight", a.norm_k, "weight")
+            self._set(d, i, DS["NORM_ADD_Q"], a.norm_added_q.weight, n + "attn.norm_added_q.weight", a.norm_added_q, "weight")
+            self._set(d, i, DS["NORM_ADD_K"], a.norm_added_k.weight, n + "attn.norm_added_k.weight", a.norm_added_k, "weight")
             self._lin(d, i, DS, "OUT", a.to_out[0], n + "attn.to_out.0")
             self._lin(d, i, DS, "ADD_OUT", a.to_add_out, n + "attn.to_add_out")
             self._lin(d, i, DS, "FF_UP", b.img_mlp.net[0].proj, n + "img_mlp.net.0.proj")

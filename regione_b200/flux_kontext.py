@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import FluxEngine
+from .engine import FluxEngine, cached_engine
 from .manager import RegionManager, plan_steps
 from .params import GAMMA, SCALAR_ROUNDS_TO_BF16
 from .schedule import calculate_shift, retrieve_timesteps
@@ -127,26 +127,19 @@ class RegionESchedulerMixin:
 
 # ---------------------------------------------------------------------------------------------- patched forward
 def _get_engine(transformer, T, L, C, n_pass=1) -> FluxEngine:
-    cache = transformer.__dict__.setdefault("_regione_b200_engines", {})
-    key = (T, L, C, n_pass)
-    eng = cache.get(key)
-    if eng is None:
-        for old in list(cache.values()):   # one resident KV cache per transformer: shapes rarely change
-            old.close()
-        cache.clear()
-        eng = FluxEngine(transformer, T, L, C, n_pass)
-        cache[key] = eng
-    return eng
+    return cached_engine(transformer, (T, L, C, n_pass), lambda: FluxEngine(transformer, T, L, C, n_pass))
 
 
 def RegionEFluxTransformer2DModelforward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None,
                                          timestep=None, img_ids=None, txt_ids=None, guidance=None,
                                          joint_attention_kwargs=None, controlnet_block_samples=None,
                                          controlnet_single_block_samples=None, return_dict=True,
-                                         controlnet_blocks_repeat=False):
-    """Same signature as the reference's patched forward (inplace.py:413-427). Mode selection follows the
-    processor's rule (inplace.py:717-732): all L+C image tokens present -> FULL (cache rows of every token are
-    rewritten); fewer -> REGION with selection = MANAGER.edited_ids."""
+                                         controlnet_blocks_repeat=False, condition_latents=None):
+    """Same signature as the reference's patched forward (inplace.py:413-427) plus `condition_latents`: on FULL steps
+    the loop hands the instruction-image latent separately ([1,C,64]) and the library reads the two row ranges in
+    place, instead of `torch.cat([latents, image_latents], dim=1)` (inplace.py:332; a concatenated `hidden_states` is
+    still accepted). Mode selection follows the processor's rule (inplace.py:717-732): all L+C image tokens present
+    -> FULL (cache rows of every token are rewritten); fewer -> REGION with selection = MANAGER.edited_ids."""
     if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
         raise NotImplementedError("regione_b200: ControlNet residuals are outside the hot path")
     if joint_attention_kwargs and "ip_adapter_image_embeds" in joint_attention_kwargs:
@@ -159,14 +152,15 @@ def RegionEFluxTransformer2DModelforward(self, hidden_states, encoder_hidden_sta
     M = MANAGER
     t_x1000 = float((timestep.to(hidden_states.dtype) * 1000).reshape(-1)[0])                    # :471
     x = hidden_states[0]
-    full = x.shape[0] == M.latent_length + M.condition_length
+    x_cond = None if condition_latents is None else condition_latents[0]
+    full = x.shape[0] + (0 if x_cond is None else x_cond.shape[0]) == M.latent_length + M.condition_length
     if full:
         sel, n_out = None, M.latent_length
     else:
-        if M.edited_ids is None or x.shape[0] != M.edited_ids.numel():
+        if x_cond is not None or M.edited_ids is None or x.shape[0] != M.edited_ids.numel():
             raise RuntimeError("regione_b200: region step without a matching edited-token selection")
         sel, n_out = M.edited_ids, x.shape[0]
-    out = engine.step(x, sel, t_x1000, n_out)[None]
+    out = engine.step(x, sel, t_x1000, n_out, x_cond=x_cond)[None]
     if not return_dict:
         return (out,)
     return types.SimpleNamespace(sample=out)
@@ -186,8 +180,22 @@ class RegionEFluxKontextPipelineMixin:
                  max_sequence_length=512, max_area=1024 ** 2, _auto_resize=True, image_latents=None,
                  true_cfg_scale=1.0, **unused):
         assert num_inference_steps == MANAGER.inference_step, "num_inference_steps should be equal to 28"   # :112
-        if true_cfg_scale > 1:
-            raise NotImplementedError("regione_b200: true-CFG needs a second pass; not wired for FluxKontext yet")
+        # arguments of the reference's __call__ that this path does not implement are rejected, not swallowed
+        has_neg_prompt = any(unused.get(k) is not None for k in ("negative_prompt", "negative_prompt_embeds"))   # :176
+        if true_cfg_scale > 1 and has_neg_prompt:                                                           # :180
+            raise NotImplementedError("regione_b200: true-CFG (a negative prompt with true_cfg_scale > 1) needs a "
+                                      "second forward per step; not wired for FluxKontext")
+        for k in ("ip_adapter_image", "ip_adapter_image_embeds", "negative_ip_adapter_image",
+                  "negative_ip_adapter_image_embeds", "callback_on_step_end", "sigmas"):
+            if unused.get(k) is not None:
+                raise NotImplementedError(f"regione_b200: `{k}` is outside the hot path and not supported")
+        known = {"negative_prompt", "negative_prompt_2", "negative_prompt_embeds", "negative_pooled_prompt_embeds",
+                 "ip_adapter_image", "ip_adapter_image_embeds", "negative_ip_adapter_image",
+                 "negative_ip_adapter_image_embeds", "callback_on_step_end", "callback_on_step_end_tensor_inputs",
+                 "sigmas"}
+        extra = set(unused) - known
+        if extra:
+            raise TypeError(f"__call__() got unexpected keyword arguments {sorted(extra)}")
         device = self._execution_device
         multiple_of = self.vae_scale_factor * 2
         self._guidance_scale = guidance_scale
@@ -207,6 +215,12 @@ class RegionEFluxKontextPipelineMixin:
                 image = self.image_processor.resize(image, ih, iw)
                 image = self.image_processor.preprocess(image, ih, iw)
                 height, width = image.shape[-2], image.shape[-1]
+            else:                                                                                  # :133-144
+                height = height or self.default_sample_size * self.vae_scale_factor
+                width = width or self.default_sample_size * self.vae_scale_factor
+                aspect_ratio = width / height
+                width = round((max_area * aspect_ratio) ** 0.5) // multiple_of * multiple_of
+                height = round((max_area / aspect_ratio) ** 0.5) // multiple_of * multiple_of
             prompt_embeds, pooled_prompt_embeds, text_ids = self.encode_prompt(
                 prompt=prompt, prompt_2=prompt_2, prompt_embeds=prompt_embeds,
                 pooled_prompt_embeds=pooled_prompt_embeds, device=device, num_images_per_prompt=num_images_per_prompt,
@@ -280,13 +294,12 @@ class RegionEFluxKontextPipelineMixin:
             else:
                 cur = M.current_step
                 full = cur <= M.warmup_step - 1 or cur > N - M.post_step - 1 or cur == M.prev_refresh_step   # :331
-                x_in = torch.cat([x, cond], dim=0) if full else x
                 timestep = t.expand(1).to(x.dtype)                                                # :334
-                noise_pred = self.transformer(hidden_states=x_in[None], timestep=timestep / 1000, guidance=guidance,
+                noise_pred = self.transformer(hidden_states=x[None], timestep=timestep / 1000, guidance=guidance,
                                               pooled_projections=pooled_prompt_embeds,
                                               encoder_hidden_states=prompt_embeds, txt_ids=text_ids,
-                                              img_ids=latent_ids, joint_attention_kwargs=None,
-                                              return_dict=False)[0]
+                                              img_ids=latent_ids, joint_attention_kwargs=None, return_dict=False,
+                                              condition_latents=image_latents if full else None)[0]   # :331-332
                 noise_pred = noise_pred[0, : x.shape[0]]                                          # :347
                 cache = noise_pred                                                                # :365
                 x = sch.step(noise_pred, t, x, return_dict=False)[0]                               # :369

@@ -39,8 +39,20 @@ class RegionEHelper(object):
         self.pipeline = _family(self.name).unwarp_modules(self.pipeline)
 
     def set_params(self, num_inference_steps=28, warmup_step=None, post_step=None, refresh_step=None, threshold=None,
-                   cache_threshold=None, erosion_dilation=None):
-        assert num_inference_steps == 28, "num_inference_steps must be 28"
+                   cache_threshold=None, erosion_dilation=None, gamma=None):
+        """RegionE.py:43-51. One extension: the reference fixes 28 steps because its gamma tables have 27 fitted
+        entries ("Changing the inference step requires fitting a new gamma", utils.py:391). Here the table is an
+        input: `gamma` (num_inference_steps - 1 entries) lifts the 28-step restriction (BASELINE configs[2]: Qwen,
+        20 steps). Without `gamma` the reference's assertion holds unchanged."""
+        if gamma is None:
+            assert num_inference_steps == 28, "num_inference_steps must be 28"
+            self.config.pop("gamma", None)
+            self.config["num_inference_steps"] = 28
+        else:
+            gamma = [float(g) for g in gamma]
+            assert len(gamma) == num_inference_steps - 1, "gamma needs num_inference_steps - 1 entries"
+            self.config["gamma"] = gamma
+            self.config["num_inference_steps"] = int(num_inference_steps)
         for key, value in (("warmup_step", warmup_step), ("post_step", post_step), ("refresh_step", refresh_step),
                            ("threshold", threshold), ("cache_threshold", cache_threshold),
                            ("erosion_dilation", erosion_dilation)):

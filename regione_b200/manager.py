@@ -32,6 +32,7 @@ class RegionManager:
         self.threshold = None
         self.cache_threshold = 0
         self.refresh_step = []
+        self.gamma = None            # caller-supplied table (None: the family's fitted 27-entry table)
         # realtime data
         self.current_step = 0
         self.edited_ids = None       # int32 [n_e], ascending
@@ -44,8 +45,12 @@ class RegionManager:
 
     def set_parameters(self, args) -> None:
         """utils.py:390-402, same validation and the same appended sentinel."""
-        assert args["warmup_step"] >= 1 and args["num_inference_steps"] == 28, \
+        user_gamma = args.get("gamma")   # extension: a caller-supplied table lifts the 28-step restriction
+        assert args["warmup_step"] >= 1 and (args["num_inference_steps"] == 28 or user_gamma is not None), \
             "Changing the inference step requires fitting a new gamma"
+        assert user_gamma is None or len(user_gamma) == args["num_inference_steps"] - 1, \
+            "gamma needs num_inference_steps - 1 entries"
+        self.gamma = None if user_gamma is None else [float(g) for g in user_gamma]
         self.inference_step = args["num_inference_steps"]
         self.warmup_step = args["warmup_step"]
         self.post_step = args["post_step"]
@@ -78,12 +83,17 @@ class RegionManager:
 
     # -- split / merge of the latent rows (utils.py:404-435)
     def _split(self, latent, latent_ids):
+        """utils.py:407-410 / :429-432. The reference also gathers `latent_ids` down to the edited rows; the only
+        consumer of those ids is the patched forward's rotary lookup, which here goes through `edited_ids` itself
+        (the library looks query rows up in the full table through the selection), so no id tensor is gathered and
+        the loop carries None until the next merge."""
         self.unedited_latent = ops.gather_rows(latent, self.unedited_ids)
-        ids = latent_ids.index_select(0, self.edited_ids.long()) if latent_ids is not None else None
-        return ops.gather_rows(latent, self.edited_ids), ids
+        return ops.gather_rows(latent, self.edited_ids), None
 
     def _merge(self, latent):
-        full = torch.zeros(self.latent_length, latent.shape[1], dtype=latent.dtype, device=latent.device)
+        """utils.py:412-418 / :421-426: edited and unedited ids partition [0, L), so every row of the result is
+        written by exactly one of the two scatters and no zero fill is needed."""
+        full = torch.empty(self.latent_length, latent.shape[1], dtype=latent.dtype, device=latent.device)
         ops.scatter_rows(latent, self.edited_ids, full)
         ops.scatter_rows(self.unedited_latent, self.unedited_ids, full)
         return full, self.latent_ids
@@ -114,6 +124,9 @@ def plan_steps(timesteps_host: torch.Tensor, gamma, manager: RegionManager):
     (skip: bool, ratio: float | None).
     """
     N, warm, post = manager.inference_step, manager.warmup_step, manager.post_step
+    if manager.gamma is not None:      # caller-supplied table (set_params(gamma=...)); else the family's fitted one
+        gamma = manager.gamma
+    assert len(gamma) == N - 1, "gamma needs num_inference_steps - 1 entries"
     g = torch.tensor(gamma, dtype=torch.float16)
     ts = timesteps_host.detach().to("cpu", torch.float32)
     rt = list(manager.refresh_step)

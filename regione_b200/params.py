@@ -39,3 +39,19 @@ GAMMA = {
 # common dtype); the reference's dt, dt_final and AVDC ratio all pass through such a product (inplace.py:318, 650,
 # 655-680). Measured on the B200 box with tools/scalar_semantics.py.
 SCALAR_ROUNDS_TO_BF16 = True
+
+
+def resample_gamma(table, num_inference_steps: int):
+    """A fitted 27-entry (28-step) table linearly resampled to `num_inference_steps - 1` entries over the normalised
+    step index (the stand-in for a 20-step run, for which the reference ships no table).
+    NOT a fitted table: results with it are unpinned with respect to the reference."""
+    n_src, n_dst = len(table), num_inference_steps - 1
+    if n_dst == n_src:
+        return list(table)
+    out = []
+    for j in range(n_dst):
+        pos = j * (n_src - 1) / max(n_dst - 1, 1)
+        lo = min(int(pos), n_src - 2)
+        f = pos - lo
+        out.append(round((1 - f) * table[lo] + f * table[lo + 1], 4))
+    return out

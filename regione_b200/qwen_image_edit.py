@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .engine import cached_engine
 from .engine_qwen import QwenEngine
 from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
@@ -27,23 +28,16 @@ MANAGER = RegionManager()                     # :51
 
 
 def _get_engine(transformer, T, L, C) -> QwenEngine:
-    cache = transformer.__dict__.setdefault("_regione_b200_engines", {})
-    key = (T, L, C, 2)
-    eng = cache.get(key)
-    if eng is None:
-        for old in list(cache.values()):
-            old.close()
-        cache.clear()
-        eng = QwenEngine(transformer, T, L, C, n_pass=2)
-        cache[key] = eng
-    return eng
+    return cached_engine(transformer, (T, L, C, 2), lambda: QwenEngine(transformer, T, L, C, n_pass=2))
 
 
 def RegionEQwenImageTransformer2DModelforward(self, hidden_states, encoder_hidden_states=None,
                                               encoder_hidden_states_mask=None, timestep=None, img_shapes=None,
                                               txt_seq_lens=None, guidance=None, attention_kwargs=None,
-                                              controlnet_block_samples=None, latent_ids=None, return_dict=True):
-    """Signature of the reference's patched forward (QwenImageEdit/inplace.py:462-475). `attention_kwargs['tag']`
+                                              controlnet_block_samples=None, latent_ids=None, return_dict=True,
+                                              condition_latents=None):
+    """Signature of the reference's patched forward (QwenImageEdit/inplace.py:462-475) plus `condition_latents` (FULL
+    steps: the instruction-image latent, read in place instead of concatenated, :366-367). `attention_kwargs['tag']`
     selects the pass ('cond' -> cache set 0, 'uncond' -> cache set 1), as in the processor (:747, :784)."""
     if controlnet_block_samples is not None:
         raise NotImplementedError("regione_b200: ControlNet residuals are outside the hot path")
@@ -59,14 +53,15 @@ def RegionEQwenImageTransformer2DModelforward(self, hidden_states, encoder_hidde
     # time_proj has scale 1000 (diffusers Timesteps(scale=1000)); the bf16 timestep is what the reference feeds (:517)
     t_x1000 = float(timestep.to(hidden_states.dtype).float().reshape(-1)[0]) * 1000.0
     x = hidden_states[0]
-    full = x.shape[0] == M.latent_length + M.condition_length
+    x_cond = None if condition_latents is None else condition_latents[0]
+    full = x.shape[0] + (0 if x_cond is None else x_cond.shape[0]) == M.latent_length + M.condition_length
     if full:
         sel, n_out = None, M.latent_length
     else:
-        if M.edited_ids is None or x.shape[0] != M.edited_ids.numel():
+        if x_cond is not None or M.edited_ids is None or x.shape[0] != M.edited_ids.numel():
             raise RuntimeError("regione_b200: region step without a matching edited-token selection")
         sel, n_out = M.edited_ids, x.shape[0]
-    out = engine.step(x, sel, t_x1000, n_out, pass_id=0 if tag == "cond" else 1)[None]
+    out = engine.step(x, sel, t_x1000, n_out, pass_id=0 if tag == "cond" else 1, x_cond=x_cond)[None]
     if not return_dict:
         return (out,)
     return types.SimpleNamespace(sample=out)
@@ -152,15 +147,15 @@ class RegionEQwenImageEditPipelineMixin:
             else:
                 cur = M.current_step
                 full = cur <= M.warmup_step - 1 or cur > N - M.post_step - 1 or cur == M.prev_refresh_step   # :365
-                x_in = torch.cat([x, cond], dim=0) if full else x
                 timestep = t.expand(1).to(x.dtype)                                                   # :369
 
                 def forward(embeds, lens, tag):
-                    return self.transformer(hidden_states=x_in[None], timestep=timestep / 1000, guidance=None,
+                    return self.transformer(hidden_states=x[None], timestep=timestep / 1000, guidance=None,
                                             encoder_hidden_states_mask=None, encoder_hidden_states=embeds,
                                             img_shapes=img_shapes, txt_seq_lens=lens, latent_ids=latent_ids,
                                             attention_kwargs={**self._attention_kwargs, "tag": tag},
-                                            return_dict=False)[0][0, : x.shape[0]]
+                                            return_dict=False,
+                                            condition_latents=image_latents if full else None)[0][0, : x.shape[0]]
                 noise_pred = forward(prompt_embeds, txt_seq_lens, "cond")                            # :371-384
                 if do_cfg:                                                                           # :386-405
                     neg = forward(negative_prompt_embeds, negative_txt_seq_lens, "uncond")

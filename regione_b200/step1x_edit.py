@@ -21,7 +21,7 @@ import torch
 from . import _lib, ops
 from ._lib import G as GS
 from ._lib import check, ptr, stream_ptr
-from .engine import FluxEngine
+from .engine import FluxEngine, cached_engine
 from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
@@ -44,6 +44,7 @@ class Step1XEngine(FluxEngine):
                           device=tr.x_embedder.weight.device.index or 0, external_embed=3)
         self.cfg, self.key, self.in_channels, self.transformer = cfg, (txt_len, lat_len, cond_len, n_pass), in_ch, tr
         self._keep = []
+        self._src = []
         self._h = C.c_void_p()
         check(self.lib.rge_create(C.byref(cfg), C.byref(self._h)), "rge_create")
         try:
@@ -62,35 +63,30 @@ class Step1XEngine(FluxEngine):
         cs = torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).to(torch.float32).contiguous()
         check(self.lib.rge_begin_image_ex(self._h, pass_id, ptr(cs), None, stream_ptr()), "rge_begin_image_ex")
 
-    def step_ex(self, x_in, sel, temb, ctx, n_out, pass_id):
-        x = x_in.contiguous()
+    def step_ex(self, x_in, sel, temb, ctx, n_out, pass_id, x_cond=None):
+        x, n_x = self._rows(x_in, "latents")
+        xc, n_c = self._rows(x_cond, "condition latents")
         out = torch.empty(n_out, self.in_channels, dtype=torch.bfloat16, device=x.device)
         sel_ptr = ptr(sel)
         if sel is not None and sel.numel() == 0:
             sel_ptr = ptr(self._dummy_sel(x.device))
         temb, ctx = temb.contiguous(), ctx.contiguous()
-        check(self.lib.rge_dit_step_ex(self._h, pass_id, ptr(x) if x.numel() else None, x.shape[0], sel_ptr, ptr(temb),
-                                       ptr(ctx), ptr(out) if n_out else None, n_out, stream_ptr()), "rge_dit_step_ex")
+        check(self.lib.rge_dit_step_ex(self._h, pass_id, ptr(x) if n_x else None, n_x, ptr(xc) if n_c else None, n_c,
+                                       sel_ptr, ptr(temb), ptr(ctx), ptr(out) if n_out else None, n_out, stream_ptr()),
+              "rge_dit_step_ex")
         return out
 
 
 def _get_engine(transformer, T, L, C) -> Step1XEngine:
-    cache = transformer.__dict__.setdefault("_regione_b200_engines", {})
-    key = (T, L, C, 2)
-    eng = cache.get(key)
-    if eng is None:
-        for old in list(cache.values()):
-            old.close()
-        cache.clear()
-        eng = Step1XEngine(transformer, T, L, C)
-        cache[key] = eng
-    return eng
+    return cached_engine(transformer, (T, L, C, 2), lambda: Step1XEngine(transformer, T, L, C))
 
 
 def RegionEStep1XEditTransformer2DModelforward(self, hidden_states, encoder_hidden_states=None, timestep=None,
                                                prompt_embeds_mask=None, img_ids=None, txt_ids=None, guidance=None,
-                                               joint_attention_kwargs=None, return_dict=True, **unused):
-    """Signature of the reference's patched forward (Step1XEdit/inplace.py:459-475); batch row b runs as pass b."""
+                                               joint_attention_kwargs=None, return_dict=True, condition_latents=None,
+                                               **unused):
+    """Signature of the reference's patched forward (Step1XEdit/inplace.py:459-475) plus `condition_latents` ([1,C,64]
+    or [B,C,64], FULL steps: read in place instead of concatenated, :377-378); batch row b runs as pass b."""
     engine = self.__dict__.get("_regione_b200_engine")
     if engine is None:
         raise RuntimeError("regione_b200: no image in flight — the pipeline loop begins the image first")
@@ -102,7 +98,8 @@ def RegionEStep1XEditTransformer2DModelforward(self, hidden_states, encoder_hidd
     ts = timestep.to(dev)
     enc, y = self.connector(encoder_hidden_states, ts, prompt_embeds_mask)                        # :514-516
     temb = self.time_embed(self.time_proj(ts * 1000).to(ts)) + self.vec_embed(y)                  # :519-520
-    full = hidden_states.shape[1] == M.latent_length + M.condition_length
+    n_c = 0 if condition_latents is None else condition_latents.shape[1]
+    full = hidden_states.shape[1] + n_c == M.latent_length + M.condition_length
     if full:
         sel, n_out = None, M.latent_length
     else:
@@ -111,7 +108,8 @@ def RegionEStep1XEditTransformer2DModelforward(self, hidden_states, encoder_hidd
     cw, cb = self.context_embedder.weight.detach(), self.context_embedder.bias.detach()
     for b in range(B):
         ctx = ops.gemm(enc[b].contiguous(), cw, cb)                                               # :521
-        outs.append(engine.step_ex(hidden_states[b], sel, temb[b], ctx, n_out, b))
+        xc = None if condition_latents is None else condition_latents[min(b, condition_latents.shape[0] - 1)]
+        outs.append(engine.step_ex(hidden_states[b], sel, temb[b], ctx, n_out, b, x_cond=xc))
     out = torch.stack(outs, dim=0)
     if not return_dict:
         return (out,)
@@ -197,16 +195,16 @@ class RegionEStep1XEditPipelineMixin:
             else:
                 cur = M.current_step
                 full = cur <= M.warmup_step - 1 or cur > N - M.post_step - 1 or cur == M.prev_refresh_step   # :377
-                x_in = torch.cat([x, cond], dim=0) if full else x
                 timestep = t.expand(1).to(x.dtype)                                                # :379
                 if do_cfg:                                                                        # :381-399
-                    x_b = torch.stack((x_in, x_in), dim=0)
+                    x_b = x[None].expand(2, -1, -1)      # both batch rows read the same latent (a view, no copy)
                     timestep = torch.cat((timestep, timestep), dim=0)
                 else:
-                    x_b = x_in[None]
+                    x_b = x[None]
                 pred = self.transformer(hidden_states=x_b, timestep=timestep / 1000, guidance=None,
                                         encoder_hidden_states=embeds, prompt_embeds_mask=masks, txt_ids=text_ids,
-                                        img_ids=latent_ids, joint_attention_kwargs=None, return_dict=False)[0]
+                                        img_ids=latent_ids, joint_attention_kwargs=None, return_dict=False,
+                                        condition_latents=image_latents if full else None)[0]   # :377-378
                 pred = pred[:, : x.shape[0]]
                 if do_cfg:
                     pos, neg = pred[0], pred[1]

@@ -19,6 +19,7 @@ from . import ops
 from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
+from .engine import cached_engine
 from .step1x_edit import Step1XEngine
 from ._lib import check
 
@@ -28,22 +29,13 @@ MANAGER.neg_txt_length = None                 # utils.py:445
 
 
 def _get_engine(transformer, T, L, C) -> Step1XEngine:
-    cache = transformer.__dict__.setdefault("_regione_b200_engines", {})
-    key = (T, L, C, 2)
-    eng = cache.get(key)
-    if eng is None:
-        for old in list(cache.values()):
-            old.close()
-        cache.clear()
-        eng = Step1XEngine(transformer, T, L, C)
-        cache[key] = eng
-    return eng
+    return cached_engine(transformer, (T, L, C, 2), lambda: Step1XEngine(transformer, T, L, C))
 
 
 def RegionEStep1XEditV1P2Transformer2DModelforward(self, hidden_states, encoder_hidden_states=None, timestep=None,
                                                    prompt_embeds_mask=None, img_ids=None, txt_ids=None, guidance=None,
                                                    text_embeddings=None, text_mask=None, joint_attention_kwargs=None,
-                                                   return_dict=True, **unused):
+                                                   return_dict=True, condition_latents=None, **unused):
     """Signature of the reference's patched forward (Step1XEditV1P2/inplace.py:540-560); the tag selects the pass."""
     engine = self.__dict__.get("_regione_b200_engine")
     if engine is None:
@@ -61,9 +53,11 @@ def RegionEStep1XEditV1P2Transformer2DModelforward(self, hidden_states, encoder_
         enc = enc + self.text_token_mapping(text_embeddings) * text_mask[:, :, None].to(enc.dtype)
     temb = self.time_embed(self.time_proj(ts * 1000).to(ts)) + self.vec_embed(y)                  # :613-614
     ctx = ops.gemm(enc[0].contiguous(), self.context_embedder.weight.detach(), self.context_embedder.bias.detach())
-    full = hidden_states.shape[1] == M.latent_length + M.condition_length
+    n_c = 0 if condition_latents is None else condition_latents.shape[1]
+    full = hidden_states.shape[1] + n_c == M.latent_length + M.condition_length
     sel, n_out = (None, M.latent_length) if full else (M.edited_ids, hidden_states.shape[1])
-    out = engine.step_ex(hidden_states[0], sel, temb[0], ctx, n_out, 0 if tag == "cond" else 1)[None]
+    out = engine.step_ex(hidden_states[0], sel, temb[0], ctx, n_out, 0 if tag == "cond" else 1,
+                         x_cond=None if condition_latents is None else condition_latents[0])[None]
     if not return_dict:
         return (out,)
     return types.SimpleNamespace(sample=out)
@@ -138,16 +132,16 @@ class RegionEStep1XEditV1P2PipelineMixin:
             else:
                 cur = M.current_step
                 full = cur <= M.warmup_step - 1 or cur > N - M.post_step - 1 or cur == M.prev_refresh_step
-                x_in = torch.cat([x, cond], dim=0) if full else x
                 timestep = t.expand(1).to(x.dtype)                                               # :386
 
                 def forward(e, tag):
-                    return self.transformer(hidden_states=x_in[None], timestep=timestep / 1000, guidance=None,
+                    return self.transformer(hidden_states=x[None], timestep=timestep / 1000, guidance=None,
                                             encoder_hidden_states=e.embedding, prompt_embeds_mask=e.mask,
                                             txt_ids=e.txt_ids, img_ids=latent_ids, text_embeddings=e.text_embeds,
                                             text_mask=e.text_masks,
                                             joint_attention_kwargs={**self._joint_attention_kwargs, "tag": tag},
-                                            return_dict=False)[0][0, : x.shape[0]]
+                                            return_dict=False,
+                                            condition_latents=image_latents if full else None)[0][0, : x.shape[0]]
                 pos = forward(pe, "cond")                                                        # :388-401
                 neg = forward(ne, "uncond")                                                      # :403-419
                 if float(t) > timesteps_truncate:                                                # :421-427

@@ -1,10 +1,16 @@
 """configs[1] end to end: one complete 28-step RegionE denoise at the BASELINE shapes (FLUX.1-Kontext 1024^2: T=512,
 L=C=4096, D=3072, 24 heads, 19 + 38 blocks) through RegionEHelper / the C ABI against the oracle at the same size and
 depth (the oracle runs on the GPU box's device as the checker, with its exact fp32-softmax attention). Gates
-(north_star): identical step schedule, region mask bit-exact, relative L2 of the bf16 latents <= 1e-2 at every step."""
+(north_star): identical step schedule, region mask bit-exact, relative L2 of the bf16 latents <= 1e-2 at every step.
+
+The velocity (57 layers of bf16 rounding, no dt in front of it) is gated against a measured NOISE FLOOR: the same oracle
+run a second time with `flash_attn_func` - the function the reference itself calls (inplace.py:796-801) - in place of
+the exact fp32 softmax. Two faithful bf16 executions of the reference differ by that much at this depth; the CUDA path
+must not be further from the exact oracle than twice that distance (and never more than 3e-2)."""
 import pytest
 import torch
 
+import oracle.flux as oflux
 from oracle.flux import FluxOracle
 from oracle.loop import run_regione
 from oracle.schedule import GAMMA
@@ -35,6 +41,27 @@ def test_whole_image_at_baseline_shapes_and_depth():
                                   dict(num_inference_steps=28, **params), GAMMA["FluxKontext"], inp["latents"],
                                   inp["image_latents"], ids, torch.zeros(T, 3, device=dev), inp["prompt_embeds"],
                                   inp["pooled_prompt_embeds"], 2.5, inp["height"], inp["width"], record=True)
+    # noise floor: the oracle with the reference's own attention function (flash-attn 2.8 here, 2.8.2 pinned upstream)
+    from flash_attn import flash_attn_func
+
+    def fa(q, k, v):                       # [B,H,S,hd] as the processor holds them; flash-attn wants [B,S,H,hd]
+        o = flash_attn_func(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=False)
+        return o.reshape(o.shape[0], o.shape[1], -1)
+
+    exact = oflux.exact_attention
+    oflux.exact_attention = fa
+    try:
+        with torch.no_grad():
+            fa_out, fa_tr = run_regione(FluxOracle(w, arch["heads"], arch["n_double"], arch["n_single"], True),
+                                        dict(num_inference_steps=28, **params), GAMMA["FluxKontext"], inp["latents"],
+                                        inp["image_latents"], ids, torch.zeros(T, 3, device=dev), inp["prompt_embeds"],
+                                        inp["pooled_prompt_embeds"], 2.5, inp["height"], inp["width"], record=True)
+    finally:
+        oflux.exact_attention = exact
+    same_mask = torch.equal(fa_tr["edited_ids"], ref_tr["edited_ids"])
+    floor_v = max(rel_l2(a[0], b[0]) for a, b, m in zip(fa_tr["noise_pred"], ref_tr["noise_pred"], ref_tr["modes"])
+                  if m != "SKIP") if same_mask else float("nan")
+    floor_x = max(rel_l2(a[0], b[0]) for a, b in zip(fa_tr["latents"], ref_tr["latents"])) if same_mask else float("nan")
     helper = RegionEHelper(pipe)
     helper.set_params(**params)
     helper.enable()
@@ -54,5 +81,9 @@ def test_whole_image_at_baseline_shapes_and_depth():
     worst_v = max(rel_l2(a, b[0]) for a, b, m in zip(tr["noise_pred"], ref_tr["noise_pred"], tr["modes"]) if m != "SKIP")
     worst_x = max(rel_l2(a, b[0]) for a, b in zip(tr["latents"], ref_tr["latents"]))
     print(f"configs[1] whole image: edited {tr['edited_ids'].numel()}, worst velocity rel-L2 {worst_v:.3e}, "
-          f"worst latent rel-L2 {worst_x:.3e}, final {rel_l2(out, ref):.3e}")
+          f"worst latent rel-L2 {worst_x:.3e}, final {rel_l2(out, ref):.3e}; noise floor (oracle + flash_attn_func vs "
+          f"oracle exact, same depth): velocity {floor_v:.3e}, latent {floor_x:.3e}, same mask {same_mask}")
     assert worst_x <= 1e-2 and rel_l2(out, ref) <= 1e-2
+    assert same_mask, "the flash-attn oracle partitions differently: no floor to compare with"
+    assert worst_v <= min(3e-2, max(2.0 * floor_v, 1e-2)), \
+        f"velocity rel-L2 {worst_v:.3e} vs noise floor {floor_v:.3e}: further from the oracle than bf16 noise explains"

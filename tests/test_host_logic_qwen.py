@@ -75,3 +75,44 @@ def test_step1x_enable_disable_both_versions():
     assert pipe2.scheduler._regione_manager is s2.MANAGER and s2.gamma == params.GAMMA["Step1XEditPipelineV1P2"]
     h2.disable()
     assert pipe2.__class__ is Step1XEditPipelineV1P2
+
+
+def test_config2_step_count_and_gamma_are_inputs():
+    """BASELINE configs[2] (Qwen-Image-Edit, 20 steps, cache_threshold 0.02): the reference refuses step counts other
+    than 28 (RegionE.py:44, utils.py:391) because its tables have 27 fitted entries. Here the table is an input of
+    `set_params`; the host planner must then equal the oracle's AVDC rule evaluated with the same table (parity is
+    oracle-with-same-table only: unpinned w.r.t. the reference)."""
+    from oracle.schedule import avdc_plan, flow_match_sigmas
+    from regione_b200.manager import plan_steps
+    table = params.resample_gamma(params.GAMMA["QwenImageEditPipeline"], 20)
+    assert len(table) == 19 and table[0] == params.GAMMA["QwenImageEditPipeline"][0]
+    assert table[-1] == params.GAMMA["QwenImageEditPipeline"][-1]
+    assert params.resample_gamma(params.GAMMA["QwenImageEditPipeline"], 28) == params.GAMMA["QwenImageEditPipeline"]
+    pipe = _pipe()
+    h = RegionEHelper(pipe)
+    saved = dict(h.config)
+    try:
+        with pytest.raises(AssertionError):
+            h.set_params(num_inference_steps=20)                       # no table: the reference's assertion stands
+        with pytest.raises(AssertionError):
+            h.set_params(num_inference_steps=20, gamma=table[:-1])     # wrong length
+        h.set_params(num_inference_steps=20, cache_threshold=0.02, gamma=table)
+        h.enable()
+        try:
+            M = qw.MANAGER
+            assert M.inference_step == 20 and M.gamma == table and M.refresh_step == [16, 19]
+            _, ts = flow_match_sigmas(20, 2304)
+            got = plan_steps(ts, qw.gamma, M)
+            want = avdc_plan(ts, table, 6, 2, "16", 0.02, inference_step=20)
+            assert [s for s, _ in got] == [w["mode"] == "SKIP" for w in want]
+            for (_, r), w in zip(got, want):
+                assert (r is None) == (w["ratio"] is None) and (r is None or float(r) == w["ratio"])
+            modes = [w["mode"] for w in want]
+            assert modes[:6] == ["FULL"] * 6 and modes[15] == "FULL" and modes[18:] == ["FULL", "FULL"]
+        finally:
+            h.disable()
+        h.set_params()                                                 # back to the reference's 28-step defaults
+        assert h.config["num_inference_steps"] == 28 and "gamma" not in h.config
+    finally:
+        h.config.clear()
+        h.config.update(saved)
