@@ -30,6 +30,13 @@ PARAMS = dict(warmup_step=6, post_step=2, refresh_step="16", threshold=0.88, cac
               erosion_dilation=True)
 GRID, TXT = 64, 512            # 1024x1024 -> 64x64 latent tokens; max_sequence_length 512 (inplace.py:108)
 FULL_STEPS = 9
+# What the default workload (seed 110, rho 0.25) yields, bit-exact against the oracle at full size and depth in
+# tests/test_flux_fullimage_gpu.py: the CPU reference arm, which cannot run the partition itself, times its REGION
+# sample on this many edited tokens, so that both arms describe the same configuration.
+EDITED_TOKENS = 1064
+REGION_STEPS = 5
+WORKLOAD = ("configs[1]: FLUX.1-Kontext-dev shapes 1024x1024 (T=512, L=C=4096, D=3072, 19+38 blocks), 28 steps, "
+            "warmup_step=6 post_step=2 refresh=16 threshold=0.88 cache_threshold=0.04, bf16, 1 image stream per GPU")
 
 
 def load_traffic():
@@ -205,9 +212,12 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        per_rank = [float(ms)]
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank = [float(x) for x in every]
+        return max(per_rank), per_rank
 
     for _ in range(args.warmup):
         image_resident()
@@ -223,15 +233,39 @@ def run_ours(args):
     launches0 = lib.rge_launch_count()
     if args.profiler_range:           # ncu --profile-from-start off: capture exactly the timed images
         torch.cuda.profiler.start()
-    ms = timed(image_resident, args.steps)
+    ms, ms_ranks = timed(image_resident, args.steps)
     if args.profiler_range:
         torch.cuda.profiler.stop()
     launches = lib.rge_launch_count() - launches0
     pms, psum, pwork, pcnt = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_double * 2)(), (C.c_int64 * 2)()
     lib.rge_profile_collect(pms, psum, pwork, pcnt)
     lib.rge_profile_enable(0)
-    ms_e2e = timed(image_e2e, args.steps)
+    ms_e2e, ms_e2e_ranks = timed(image_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- multi-GPU: every rank's schedule and edited-token count, and a replica check (untimed): all ranks denoise
+    # rank 0's image (seed 110) once more and must produce bit-identical latents and the same region partition
+    replica = None
+    if world > 1:
+        mine = {"rank": rank, "schedule": "".join(m[0] for m in modes), "edited_tokens": n_edited}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        host0 = syn.make_inputs(110, grid, grid, txt, arch["ctx_dim"], arch["pooled_dim"], rho=args.rho)
+        out0 = pipe(guidance_scale=2.5, num_inference_steps=28, output_type="latent", return_dict=False,
+                    **{k: host0[k].to(dev) for k in keys}, **hw)[0]
+        torch.cuda.synchronize()
+        digest = torch.stack([out0.view(torch.int16).to(torch.int64).sum(),
+                              (out0.view(torch.int16).to(torch.int64) * torch.arange(
+                                  1, out0.numel() + 1, device=dev).view_as(out0)).sum(),
+                              torch.tensor(int(pipe.regione_trace["edited_ids"].numel()), device=dev)])
+        all_digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(all_digests, digest)
+        identical = all(torch.equal(d, all_digests[0]) for d in all_digests)
+        replica = {"per_rank": gathered, "seed_110_edited_tokens": int(all_digests[0][2]),
+                   "seed_110_bit_identical_across_ranks": bool(identical),
+                   "same_schedule_on_all_ranks": len({g["schedule"] for g in gathered}) == 1}
+        assert identical, "replicas disagree on the same input: " + str([d.tolist() for d in all_digests])
+        assert replica["same_schedule_on_all_ranks"], "ranks ran different step schedules: " + str(gathered)
 
     value = world * args.steps / (ms / 1e3)
     e2e_value = world * args.steps / (ms_e2e / 1e3)
@@ -243,14 +277,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 4), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {
-            "workload": "configs[1]: FLUX.1-Kontext-dev shapes 1024x1024 (T=512, L=C=4096, D=3072, 19+38 blocks), "
-                        "28 steps, warmup_step=6 post_step=2 refresh=16 threshold=0.88 cache_threshold=0.04, bf16, "
-                        "1 image stream per GPU" if args.arch != "tiny" else "tiny smoke configuration",
-            "schedule": "".join(m[0] for m in modes), "edited_tokens": n_edited, "rho_target": args.rho,
-            "l2": "inputs larger than L2 (23.7 GB of weights + 6 GB KV cache per image >> 126 MB)",
-            "parallelism": f"replica x{world}; NCCL all-gather of the partition mask only" if world > 1 else "1 GPU",
-        },
+        "config": workload_config(args, "".join(m[0] for m in modes), n_edited, world),
         "e2e": {"value": round(e2e_value, 4), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": round(ms_e2e / args.steps, 2)},
         "gpu_launches": int(launches),
@@ -273,17 +300,47 @@ def run_ours(args):
             "frac": round(attn_tf / peaks["tf_sustained"], 4) if attn_tf else None,
             "launches": int(pcnt[1]), "avg_launch_ms": round(psum[1] / max(pcnt[1], 1), 4),
             "share_of_step": round(pms[1] / ms, 4),
+            "note": "busy time = union of the attention launches' intervals; in the single-stream blocks the MLP GEMM "
+                    "shares the SMs with attention on purpose (tail fill), which this figure charges to attention",
         },
+        "whole_step": {"tflop_per_image": None, "achieved_tflops": None},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.arch != "tiny":
-        v, secs, desc, threads = cpu_reference_sample(n_edited, region_steps)
-        line["cpu_baseline"] = {"value": round(v, 6), "unit": "images/sec", "cores": threads, "kind": "port",
-                                "sample": desc, "measured_seconds": round(secs, 1)}
+    # whole-image arithmetic rate: algorithmic FLOPs of every launched GEMM and attention / wall time of the images
+    total_tf = (pwork[0] + pwork[1]) / 1e12 / args.steps
+    line["whole_step"] = {"tflop_per_image": round(total_tf, 1),
+                          "achieved_tflops": round(total_tf / (ms / args.steps / 1e3), 1),
+                          "frac_of_sustained_peak": round(total_tf / (ms / args.steps / 1e3) / peaks["tf_sustained"], 4)}
+    if world > 1:
+        line["per_rank_ms_per_step"] = [round(m / args.steps, 2) for m in ms_ranks]
+        line["per_rank_ms_per_step_e2e"] = [round(m / args.steps, 2) for m in ms_e2e_ranks]
+        line["replica_check"] = replica
     helper.disable()
+    if rank == 0 and world == 1 and args.arch != "tiny":
+        if not args.no_reference_gpu:
+            # the reference-equivalent eager PyTorch path on this very GPU (SURVEY §8d "how the reference path is
+            # timed (1)"): same weights (shared tensors), inputs and schedule; the north star's >= 3x is this ratio
+            ref = reference_gpu_images(args, pipe, max(args.steps, 5), 3)
+            line["reference_gpu"] = ref
+            line["speedup_vs_reference_gpu"] = {"device_resident": round(value / ref["value"], 3),
+                                                "e2e": round(e2e_value / ref["value"], 3)}
+        if not args.no_cpu_baseline:
+            v, secs, desc, threads = cpu_reference_sample(n_edited, region_steps)
+            line["cpu_baseline"] = {"value": round(v, 6), "unit": "images/sec (extrapolated from a bounded sample)",
+                                    "cores": threads, "kind": "port", "sample": desc,
+                                    "measured_seconds": round(secs, 1)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def workload_config(args, schedule: str, n_edited: int, world: int) -> dict:
+    """The `config` object both arms print (the reference arm with the workload's known schedule / edited count)."""
+    if args.arch == "tiny":
+        return {"workload": "tiny smoke configuration"}
+    return {"workload": WORKLOAD, "schedule": schedule, "edited_tokens": n_edited, "rho_target": args.rho,
+            "l2": "inputs larger than L2 (23.7 GB of weights + 6 GB KV cache per image >> 126 MB)",
+            "parallelism": f"replica x{world}; NCCL all-gather of the partition mask only" if world > 1 else "1 GPU"}
 
 
 def run_reference(args):
@@ -291,86 +348,111 @@ def run_reference(args):
     if rank != 0:
         return
     n_edited = args.ref_edited
-    region_steps = 5
     vals = []
     total = 0.0
     for i in range(args.warmup + args.steps):
-        v, secs, desc, threads = cpu_reference_sample(n_edited, region_steps)
+        v, secs, desc, threads = cpu_reference_sample(n_edited, REGION_STEPS)
         total += secs
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": "images/sec",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]: FLUX.1-Kontext-dev shapes 1024x1024, 28 steps, RegionE default schedule; "
-                               "each step = one bounded CPU sample (see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": round(v, 6), "unit": "images/sec", "cores": threads, "kind": "port", "sample": desc},
+        # the same configuration object as our arm; schedule and edited-token count are those of this workload
+        # (tests/test_flux_fullimage_gpu.py pins them against the oracle), the value is EXTRAPOLATED from the sample
+        "config": workload_config(args, "FFFFFFRSRSSRSRSFSSSSSSSRSSFF", n_edited, world),
+        "extrapolated": True,
+        "cpu_baseline": {"value": round(v, 6), "unit": "images/sec (extrapolated from a bounded sample)",
+                         "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": round(v, 6), "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def run_reference_gpu(args):
-    """EXTRA arm (not the driver's `--impl reference`): the reference-equivalent PyTorch path of SURVEY §8d on the
-    SAME GPU — the oracle restatement run in eager torch on cuda:0 with flash-attn's `flash_attn_func` where the
-    reference calls it (inplace.py:796-801) and a bf16 tensor-core GEMM + fp16 round trip where it calls its Triton
-    `_partially_linear` (fused_kernels.py:81-101; the Triton source lives in /root/reference, which does not exist on
-    the GPU box). 3 warm-up images and
-    `cuda.synchronize()` + wall clock around each image, as src/FluxKontext/main.py:49-73 does."""
+def reference_gpu_images(args, pipe, n_timed: int, n_warm: int) -> dict:
+    """The reference-equivalent PyTorch path of SURVEY §8d on the SAME GPU: the oracle restatement of the reference's
+    loop / forward / processor run in eager torch on cuda:0, calling what the reference calls where it calls it -
+    flash-attn's `flash_attn_func` (inplace.py:796-801) and the reference's OWN Triton `_partially_linear`
+    (fused_kernels.py:81-101, staged unmodified under oracle/_ref by oracle/build_ref.py; a cuBLAS GEMM + fp16 round
+    trip stands in, and says so, only if that file was never staged) - plus eager torch ops (cuBLAS nn.Linear, fp32
+    RMSNorm / RoPE over the whole cache every step, torch.cat of K / V: K-d ... K-g of SURVEY §2.2). Same weights
+    (the very tensors of `pipe`), inputs and schedule as our arm; `n_warm` warm-up images, then `cuda.synchronize()` +
+    wall clock around each image exactly like src/FluxKontext/main.py:49-73."""
     import torch.nn.functional as F
     import oracle.flux as of
     from flash_attn import flash_attn_func
+    from oracle.build_ref import load_partially_linear
     from oracle.loop import run_regione
     from oracle.schedule import GAMMA
     from regione_b200 import synthetic as syn
     from regione_b200.standin import latent_image_ids
 
-    dev = torch.device("cuda", 0)
+    dev = pipe.transformer.x_embedder.weight.device
 
     def fa(q, k, v):                       # [B,H,S,hd] like the processor after RoPE; flash-attn wants [B,S,H,hd]
         o = flash_attn_func(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=False)
         return o.reshape(o.shape[0], o.shape[1], -1)
 
-    def pl(x, w, b, index, cache):
+    triton_pl = None if args.ref_no_triton else load_partially_linear()
+
+    def pl_cublas(x, w, b, index, cache):
         cache[:, index, :] = F.linear(x, w, b).to(torch.float16).to(cache.dtype)
 
-    of.exact_attention, of.partially_linear = fa, pl
-    arch = syn.FLUX_KONTEXT
-    pipe = syn.build_pipeline(arch, seed=110, device=dev)
-    w = {k: v.detach() for k, v in pipe.transformer.state_dict().items()}
-    model = of.FluxOracle(w, arch["heads"], arch["n_double"], arch["n_single"], True)
-    inp = syn.make_inputs(110, GRID, GRID, TXT, arch["ctx_dim"], arch["pooled_dim"], rho=args.rho, device=dev)
-    ids = torch.cat([latent_image_ids(GRID, GRID, 0.0, dev), latent_image_ids(GRID, GRID, 1.0, dev)])
-    txt_ids = torch.zeros(TXT, 3, device=dev)
+    def pl_triton(x, w, b, index, cache):
+        triton_pl(x.contiguous(), w, b, index, cache)
 
-    def image():
-        with torch.no_grad():
-            return run_regione(model, dict(num_inference_steps=28, **PARAMS), GAMMA["FluxKontext"], inp["latents"],
-                               inp["image_latents"], ids, txt_ids, inp["prompt_embeds"], inp["pooled_prompt_embeds"],
-                               2.5, inp["height"], inp["width"])
+    saved = of.exact_attention, of.partially_linear
+    of.exact_attention, of.partially_linear = fa, (pl_triton if triton_pl is not None else pl_cublas)
+    try:
+        arch = syn.FLUX_KONTEXT
+        w = {k: v.detach() for k, v in pipe.transformer.state_dict().items()}
+        model = of.FluxOracle(w, arch["heads"], arch["n_double"], arch["n_single"], True)
+        inp = syn.make_inputs(110, GRID, GRID, TXT, arch["ctx_dim"], arch["pooled_dim"], rho=args.rho, device=dev)
+        ids = torch.cat([latent_image_ids(GRID, GRID, 0.0, dev), latent_image_ids(GRID, GRID, 1.0, dev)])
+        txt_ids = torch.zeros(TXT, 3, device=dev)
 
-    for _ in range(args.warmup):
-        out, tr = image()
-    times = []
-    for _ in range(args.steps):
-        torch.cuda.synchronize()
-        t0 = time.time()
-        out, tr = image()
-        torch.cuda.synchronize()
-        times.append(time.time() - t0)
+        def image():
+            with torch.no_grad():
+                return run_regione(model, dict(num_inference_steps=28, **PARAMS), GAMMA["FluxKontext"],
+                                   inp["latents"], inp["image_latents"], ids, txt_ids, inp["prompt_embeds"],
+                                   inp["pooled_prompt_embeds"], 2.5, inp["height"], inp["width"])
+
+        for _ in range(n_warm):
+            out, tr = image()
+        times = []
+        for _ in range(n_timed):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            out, tr = image()
+            torch.cuda.synchronize()
+            times.append(time.time() - t0)
+    finally:
+        of.exact_attention, of.partially_linear = saved
     sec = sum(times) / len(times)
+    return {"value": round(1.0 / sec, 4), "unit": "images/sec", "ms": round(sec * 1e3, 1),
+            "per_image_s": [round(t, 4) for t in times], "warmup_images": n_warm,
+            "attention": "flash_attn_func (flash-attn %s)" % __import__("flash_attn").__version__,
+            "partially_linear": ("reference Triton kernel (oracle/_ref/fused_kernels.py, triton %s)"
+                                 % __import__("triton").__version__) if triton_pl is not None
+                                else "cuBLAS GEMM + fp16 round trip (oracle/_ref not staged)",
+            "schedule": "".join(m[0] for m in tr["modes"]), "edited_tokens": int(tr["edited_ids"].numel()),
+            "timing": "cuda.synchronize() + wall clock per image, as src/FluxKontext/main.py:62-73"}
+
+
+def run_reference_gpu(args):
+    """`--impl reference_gpu`: only the reference-equivalent GPU arm (the default N = 1 run of our arm embeds it)."""
+    from regione_b200 import synthetic as syn
+    pipe = syn.build_pipeline(syn.FLUX_KONTEXT, seed=110, device=torch.device("cuda", 0))
+    ref = reference_gpu_images(args, pipe, args.steps, args.warmup)
     print(json.dumps({
-        "impl": "reference_gpu", "metric": METRIC, "value": round(1.0 / sec, 4), "unit": "images/sec", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True,
+        "impl": "reference_gpu", "metric": METRIC, "value": ref["value"], "unit": "images/sec", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ref["ms"], "higher_is_better": True,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]; reference-equivalent eager PyTorch path on the same B200: oracle "
-                               "restatement + flash_attn_func (flash-attn 2.8) + cuBLAS bf16; same weights, inputs, "
-                               "schedule as our arm", "schedule": "".join(m[0] for m in tr["modes"]),
-                   "edited_tokens": int(tr["edited_ids"].numel()), "rho_target": args.rho},
-        "per_image_s": [round(t, 4) for t in times]}))
+        "config": workload_config(args, ref["schedule"], ref["edited_tokens"], 1), "reference_gpu": ref}))
 
 
 def main():
@@ -381,8 +463,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
     ap.add_argument("--rho", type=float, default=0.25, help="target edited fraction of the synthetic image")
     ap.add_argument("--arch", default="flux", choices=["flux", "tiny"])
-    ap.add_argument("--ref-edited", type=int, default=1200, help="edited tokens of the CPU reference sample")
+    ap.add_argument("--ref-edited", type=int, default=EDITED_TOKENS,
+                    help="edited tokens of the CPU reference sample (default: what the default workload yields)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the reference-equivalent PyTorch arm on the same GPU (N = 1 runs embed it by default)")
+    ap.add_argument("--ref-no-triton", action="store_true",
+                    help="reference GPU arm: cuBLAS + fp16 round trip instead of the staged Triton _partially_linear")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed (device-resident) images, for ncu launch lists")
     args = ap.parse_args()

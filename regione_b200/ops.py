@@ -19,7 +19,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def _gemm_desc(d, a, w, bias=None, *, epilogue=_lib.EPI_STORE, out=None, row_map=None, row_off=0, col_off=0, gate=None,
-               res=None, norm_w=None, rope_cs=None, rope_map=None, rope_off=0):
+               res=None, norm_w=None, rope_cs=None, rope_map=None, rope_off=0, rope_ld=0, fp16_roundtrip=False):
     _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
     M, K = a.shape
     N = w.shape[0]
@@ -36,6 +36,8 @@ def _gemm_desc(d, a, w, bias=None, *, epilogue=_lib.EPI_STORE, out=None, row_map
     d.gate, d.res, d.ldr = ptr(gate), ptr(res), (res.stride(0) if res is not None else 0)
     d.norm_w, d.rope_cs = ptr(norm_w), ptr(rope_cs)
     d.rope_map, d.rope_off = ptr(rope_map), rope_off
+    d.rope_ld = rope_ld              # 0: rope_cs is [S,64,2]; > 0: pair-major [64, rope_ld, 2]
+    d.flags = _lib.GEMM_FP16_ROUNDTRIP if fp16_roundtrip else 0
     return out
 
 
@@ -55,6 +57,12 @@ def gemm_group(members):
     outs = [_gemm_desc(descs[i], a, w, bias, **kw) for i, (a, w, bias, kw) in enumerate(members)]
     check(lib.rge_op_gemm_group(descs, len(members), stream_ptr()), "rge_op_gemm_group")
     return outs
+
+
+def set_option(name: str, value: int) -> None:
+    """Run-time tuning knob of the kernels (rge_set_option): "attn_poly", "attn_split", "gemm_bn", "2cta_min_m",
+    "raster"."""
+    check(_lib.load().rge_set_option(name.encode(), int(value)), f"rge_set_option({name})")
 
 
 def attention(q, k, v, heads: int, out=None, scale: float | None = None):

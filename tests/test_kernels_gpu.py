@@ -177,6 +177,25 @@ def test_gemm_norm_rope_epilogue_matches_oracle():
     x = of.apply_rope(of.rms_norm(x, nw), (cos[pos + 7], sin[pos + 7]))
     ref = x.transpose(1, 2).reshape(M, N)
     assert rel_l2(cache[rows], ref) <= BF16_TOL
+    # the pair-major table layout the engine keeps ([64][ld]: one rotary pair of consecutive rows is contiguous, so an
+    # epilogue warp reads it coalesced) must give bit-identical results, on both the 1-CTA and the CTA-pair kernel
+    ld = S + 12
+    cs_pm = torch.zeros(64, ld, 2, device="cuda")
+    cs_pm[:, :S] = cs.permute(1, 0, 2)
+    cache_pm = torch.zeros(S, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, b, epilogue=_lib.EPI_NORM_ROPE, out=cache_pm, row_map=rows.int(), norm_w=nw, rope_cs=cs_pm,
+             rope_map=pos.int(), rope_off=7, rope_ld=ld)
+    assert torch.equal(cache_pm, cache)
+    M2 = 2304                                                       # >= 2048 rows: CTA-pair kernel
+    a2 = torch.randn(M2, K, device="cuda", generator=g).bfloat16()
+    pos2 = torch.randint(0, S - 7, (M2,), device="cuda", generator=g)
+    out_rm = ops.gemm(a2, w, b, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=pos2.int(), rope_off=7)
+    out_pm = ops.gemm(a2, w, b, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_map=pos2.int(), rope_off=7,
+                      rope_ld=ld)
+    assert torch.equal(out_rm, out_pm)
+    x2 = F.linear(a2, w, b).view(1, M2, H, 128).transpose(1, 2)
+    x2 = of.apply_rope(of.rms_norm(x2, nw), (cos[pos2 + 7], sin[pos2 + 7]))
+    assert rel_l2(out_pm, x2.transpose(1, 2).reshape(M2, N)) <= BF16_TOL
 
 
 @pytest.mark.parametrize("Sq,Skv,H", [(256, 256, 1), (128, 128, 2), (1, 130, 1), (200, 544, 2), (700, 1300, 3),
@@ -192,6 +211,31 @@ def test_attention_matches_exact_softmax(Sq, Skv, H):
     hd = lambda t: t.view(1, -1, H, 128).transpose(1, 2)          # noqa: E731
     ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
     assert rel_l2(o, ref) <= 6e-3                                  # bf16 P and bf16 output
+
+
+@pytest.mark.parametrize("poly", [0, 2, 3, 4])
+def test_attention_exponential_offload_variants(poly):
+    """`attn_poly` of every 8 exponential pairs run as a Cody-Waite / degree-3 polynomial on the FMA pipe instead of
+    MUFU.EX2 (relative error 7.5e-5, below the bf16 rounding of P): every variant stays within the same tolerance of
+    the exact softmax, including rows with large late keys (lazy rescale) and a ragged KV tail (masked columns)."""
+    from regione_b200 import ops
+    g = _gen(21)
+    Sq, Skv, H = 777, 2100, 3
+    q = torch.randn(Sq, H * 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(Skv, H * 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(Skv, H * 128, device="cuda", generator=g).bfloat16()
+    k[Skv // 2:] *= 3.0
+    q[:64] *= 6.0                                                   # peaked rows: scores far below the row maximum
+    hd = lambda t: t.view(1, -1, H, 128).transpose(1, 2)          # noqa: E731
+    ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
+    ops.set_option("attn_poly", poly)
+    try:
+        o = ops.attention(q, k, v, H)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("attn_poly", -1)
+    assert torch.isfinite(o.float()).all()
+    assert rel_l2(o, ref) <= 6e-3
 
 
 @pytest.mark.parametrize("Sq,Skv,H", [(1576, 8704, 4), (8704, 8704, 2), (333, 1000, 3)])
