@@ -448,10 +448,13 @@ struct StepRun {
     return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
   }
 
-  int attention(bf16* kc, bf16* vc, cudaStream_t sa) const {
+  // queries = rows [row0, row0 + n_rows) of the [text; image] sequence (default: all active rows)
+  int attention(bf16* kc, bf16* vc, cudaStream_t sa, int row0 = 0, int n_rows = -1) const {
     AttnArgs at;
-    at.Q = h->q; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D; at.O = h->big; at.ldo = ldb;
-    at.Sq = MA; at.Skv = S; at.H = h->H;
+    at.Q = h->q + (size_t)row0 * D; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D;
+    at.O = h->big + (size_t)row0 * ldb; at.ldo = ldb;
+    at.Sq = n_rows < 0 ? MA : n_rows; at.Skv = S; at.H = h->H;
+    if (at.Sq <= 0) return RGE_OK;
     ProfScope prof(sa, PC_ATTN, 4.0 * at.Sq * (double)at.Skv * 128.0 * at.H, at.Sq, at.Skv, at.H);
     RGE_LAUNCH(launch_attention(at, sa));
     return RGE_OK;
@@ -649,6 +652,67 @@ struct StepRun {
     }
     RGE_CUDA(link(sT, h->ev_aux[0], st));
     return one(st, s_out(b, mod + 2 * D));
+  }
+
+  // ---- LAST block of the stack: only the first n_out image rows (the noise tokens) reach norm_out / proj_out; the
+  // text rows and the instruction-image rows are discarded after it (inplace.py:347, :566-567). K / V still need every
+  // row (attention runs over all keys), but queries, attention output, MLP and the output projections are computed for
+  // those n_out rows only. Rows are independent in every one of these ops, so the kept rows are bit-identical.
+  int single_block_last(int b, int layer, const bf16* mod, int n_out) const {
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, mod + D, mod, h->n, D, MA, D, st));
+    RGE_CUDA(link(st, h->ev_main, sK));
+    RGE_CUDA(link(st, h->ev_main, sV));
+    RGE_CUDA(link(st, h->ev_main, sT));
+    GemmArgs q = s_q(b);
+    q.A = n_img_p; q.M = n_out; q.row_off = T; q.rope_map = h->sel_all + T;
+    RGE_TRY(one(st, q));
+    RGE_TRY(one(sK, s_k(b, kc)));
+    RGE_TRY(one(sV, s_v(b, vc)));
+    GemmArgs mlp = s_mlp(b);
+    mlp.A = n_img_p; mlp.M = n_out; mlp.out = big_img;
+    RGE_TRY(one(sT, mlp));
+    RGE_CUDA(link(sK, h->ev_aux[1], st));
+    RGE_CUDA(link(sV, h->ev_aux[2], st));
+    RGE_TRY(attention(kc, vc, st, T, n_out));
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    GemmArgs o = s_out(b, mod + 2 * D);
+    o.A = big_img; o.M = n_out; o.out = x_img; o.res = x_img;
+    return one(st, o);
+  }
+
+  int double_block_last(int b, int layer, const bf16* mod, int n_out) const {
+    const bf16* cm = mod + 6 * D;
+    bf16* kc = h->kc(pass, layer);
+    bf16* vc = h->vc(pass, layer);
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + D, mod, n_img_p, D, M, D, st));
+    RGE_CUDA(link(st, h->ev_main, sK));
+    RGE_CUDA(link(st, h->ev_main, sV));
+    GemmArgs q = img_q(b);
+    q.M = n_out;
+    RGE_TRY(one(st, q));
+    RGE_TRY(one(sK, img_k(b, kc)));
+    RGE_TRY(one(sV, img_v(b, vc)));
+    // text keys / values are still attended to; text queries and the whole text chain after attention are not needed
+    RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
+    RGE_CUDA(link(sT, h->ev_txt, sTV));
+    RGE_TRY(one(sT, txt_k(b, kc)));
+    RGE_TRY(one(sTV, txt_v(b, vc)));
+    RGE_CUDA(link(sT, h->ev_aux[0], st));
+    RGE_CUDA(link(sK, h->ev_aux[1], st));
+    RGE_CUDA(link(sV, h->ev_aux[2], st));
+    RGE_CUDA(link(sTV, h->ev_aux[4], st));
+    RGE_TRY(attention(kc, vc, st, T, n_out));
+    GemmArgs o = img_out(b, mod + 2 * D);
+    o.M = n_out;
+    RGE_TRY(one(st, o));
+    RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + 4 * D, mod + 3 * D, n_img_p, D, n_out, D, st));
+    GemmArgs up = img_up(b), down = img_down(b, mod + 5 * D);
+    up.M = n_out;
+    down.M = n_out;
+    RGE_TRY(one(st, up));
+    return one(st, down);
   }
 
   int single_block_grouped(int b, int layer, const bf16* mod) const {
@@ -943,11 +1007,19 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   // GEMMs of a stage fan out over the side streams (the default: see rge_handle::grouped).
   const bool grouped = h->grouped && r.MA < 2048;
   if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(st, h->ev_main, r.sT));
+  // the last block of the stack computes only the rows whose output survives (bit-identical; tuning().trim_last)
+  const bool trim = tuning().trim_last && h->fanout && !grouped && n_out < MA;
+  const int last_double = trim && h->cfg.n_single == 0 ? h->cfg.n_double - 1 : -1;
+  const int last_single = trim ? h->cfg.n_single - 1 : -1;
   for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D)
-    RGE_TRY(grouped ? r.double_block_grouped(b, layer, mod) : r.double_block_fanout(b, layer, mod));
+    RGE_TRY(b == last_double ? r.double_block_last(b, layer, mod, n_out)
+            : grouped        ? r.double_block_grouped(b, layer, mod)
+                             : r.double_block_fanout(b, layer, mod));
   if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(r.sT, h->ev_aux[0], st));
   for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D)
-    RGE_TRY(grouped ? r.single_block_grouped(b, layer, mod) : r.single_block_fanout(b, layer, mod));
+    RGE_TRY(b == last_single ? r.single_block_last(b, layer, mod, n_out)
+            : grouped        ? r.single_block_grouped(b, layer, mod)
+                             : r.single_block_fanout(b, layer, mod));
   bf16* x_img = r.x_img;
   bf16* n_img_p = r.n_img_p;
   // ---- norm_out (scale first, then shift) + proj_out on the noise rows only (App. C-9)

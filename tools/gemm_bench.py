@@ -58,6 +58,12 @@ def main():
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=pos)
             fns["ours_norm_rope(pair-major table)"] = lambda: ops.gemm(
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_map=pos, rope_ld=S)
+        if M < 2048 and N % 256 == 0:        # the CTA-pair kernel below its default row threshold
+            def pair():
+                ops.set_option("2cta_min_m", 1)
+                ops.gemm(a, w, b, out=out)
+                ops.set_option("2cta_min_m", 2048)
+            fns["ours(cta-pair kernel)"] = pair
         res = {}
         for name, fn in fns.items():
             for _ in range(3):
