@@ -89,6 +89,10 @@ def _load_real(family: str, args):
         raise SystemExit(f"regione_b200.cli: --model_path {args.model_path} needs the diffusers package (fork "
                          f"Peyton-Chen/diffusers@step1xedit_v1p2, README.md:76-77), which is not installed; "
                          f"use --model_path synthetic") from e
+    if args.use_regione and FAMILIES[family][0] != "FluxKontextPipeline":
+        from .flux_kontext import LATENT_SPACE_ONLY
+        raise SystemExit("regione_b200.cli: " + LATENT_SPACE_ONLY + " Run this family with --model_path synthetic, or "
+                         "drive the patched pipeline from your own script with latents.")
     cls = getattr(diffusers, FAMILIES[family][0])
     pipe = cls.from_pretrained(args.model_path, torch_dtype=torch.bfloat16).to(args.device)
     return pipe

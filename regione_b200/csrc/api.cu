@@ -11,6 +11,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/regione_b200.h"
 #include "attention.cuh"
 #include "elementwise.cuh"
@@ -55,6 +57,22 @@ struct ProfScope {
       std::lock_guard<std::mutex> lk(g_prof_mu);
       g_recs.push_back(ProfRec{cls, work, a, b, m, n, k});
     }
+  }
+};
+
+// NVTX range (header-only nvtx3: a no-op unless a profiler injects itself) around a step / block / stage; enabled
+// with RGE_NVTX=1 or rge_set_option("nvtx", 1) so that ncu / nsys timelines can be cut by block and stage.
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* fmt, int a = 0, int b = 0) : on(tuning().nvtx != 0) {
+    if (on) {
+      char name[96];
+      snprintf(name, sizeof(name), fmt, a, b);
+      nvtxRangePushA(name);
+    }
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
   }
 };
 
@@ -533,6 +551,7 @@ struct StepRun {
 
   // adaLN vectors of a double block: image stream at mod, text stream at mod + 6 D; each shift, scale, gate x 2
   int double_block_fanout(int b, int layer, const bf16* mod) const {
+    NvtxRange range("double block %d (M=%d)", b, M);
     const bf16* cm = mod + 6 * D;
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
@@ -564,8 +583,12 @@ struct StepRun {
       RGE_CUDA(link(sTK, h->ev_aux[3], st));
       RGE_CUDA(link(sTV, h->ev_aux[4], st));
     }
-    RGE_TRY(attention(kc, vc, st));
+    {
+      NvtxRange stage("attention %d x %d", MA, S);
+      RGE_TRY(attention(kc, vc, st));
+    }
     RGE_CUDA(link(st, h->ev_main, sT));
+    NvtxRange stage("out-proj + MLP (image rows %d, text rows %d)", M, T);
     // out projection, LayerNorm, feed-forward: each stream on its own chain
     RGE_TRY(one(st, img_out(b, mod + 2 * D)));
     RGE_TRY(one(sT, txt_out(b, cm + 2 * D)));
@@ -617,6 +640,7 @@ struct StepRun {
 
   // adaLN vectors of a single block at mod: shift, scale, gate
   int single_block_fanout(int b, int layer, const bf16* mod) const {
+    NvtxRange range("single block %d (MA=%d)", b, MA);
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
     RGE_LAUNCH(launch_ln_modulate(h->h, D, mod + D, mod, h->n, D, MA, D, st));
@@ -659,6 +683,7 @@ struct StepRun {
   // row (attention runs over all keys), but queries, attention output, MLP and the output projections are computed for
   // those n_out rows only. Rows are independent in every one of these ops, so the kept rows are bit-identical.
   int single_block_last(int b, int layer, const bf16* mod, int n_out) const {
+    NvtxRange range("single block %d, last: %d rows kept", b, n_out);
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
     RGE_LAUNCH(launch_ln_modulate(h->h, D, mod + D, mod, h->n, D, MA, D, st));
@@ -683,6 +708,7 @@ struct StepRun {
   }
 
   int double_block_last(int b, int layer, const bf16* mod, int n_out) const {
+    NvtxRange range("double block %d, last: %d rows kept", b, n_out);
     const bf16* cm = mod + 6 * D;
     bf16* kc = h->kc(pass, layer);
     bf16* vc = h->vc(pass, layer);
@@ -963,6 +989,8 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
                 h->L + h->C);
   if (n_out < 0 || n_out > n_img) return fail(RGE_ERR_INVALID, "rge_dit_step: n_out %d > n_img %d", n_out, n_img);
   cudaStream_t st = (cudaStream_t)stream;
+  NvtxRange step_range(sel ? "rge_dit_step REGION (%d active image tokens, pass %d)"
+                           : "rge_dit_step FULL (%d image tokens, pass %d)", n_img, pass);
   const int D = h->D, T = h->Tp[pass], Dm = h->Dm, S = T + h->L + h->C, M = n_img, MA = T + n_img;
   const long ldb = D + Dm;  // `big`: attention output in columns [0,D), MLP hidden in [D, D+Dm)
   const float2* rope = h->rope + (size_t)pass * h->S * 64;

@@ -100,21 +100,35 @@ def merge_metrics(path: str, tasks=None) -> dict:
     """metric_merge.py:6-62: prompt-weighted mean of the per-task AVERAGE rows (metric.csv) and latencies
     (time_consuming.json, written by regione_b200.cli --evaluation); writes merged_metric.txt. A directory called
     `pretrain` (the vanilla run every other run is compared with) has no metric.csv: PSNR inf, SSIM 1, LPIPS 0."""
-    tasks = tasks or sorted(d for d in os.listdir(path) if os.path.isfile(os.path.join(path, d, "time_consuming.json")))
+    import glob
+
+    def latency_files(task):
+        # a single-process run writes time_consuming.json; a data-parallel run (torchrun, regione_b200.cli) writes one
+        # time_consuming.rank<r>.json shard per rank - the shards are summed, never mixed with a stale single file
+        shards = sorted(glob.glob(os.path.join(path, task, "time_consuming.rank*.json")))
+        single = os.path.join(path, task, "time_consuming.json")
+        return shards or ([single] if os.path.isfile(single) else [])
+
+    tasks = tasks or sorted(d for d in os.listdir(path) if os.path.isdir(os.path.join(path, d)) and latency_files(d))
     vanilla = os.path.basename(os.path.normpath(path)).lower() == "pretrain"
     sums = {"PSNR": 0.0, "SSIM": 0.0, "LPIPS": 0.0}
     items, latency = 0, 0.0
     for task in tasks:
-        with open(os.path.join(path, task, "time_consuming.json")) as f:
-            lat = json.load(f)
-        n = lat["num_item"]
+        n, task_latency = 0, 0.0
+        for name in latency_files(task):
+            with open(name) as f:
+                lat = json.load(f)
+            n += lat["num_item"]
+            task_latency += lat["ave_time_consuming"] * lat["num_item"]
         items += n
-        latency += lat["ave_time_consuming"] * n
+        latency += task_latency
         if not vanilla:
             with open(os.path.join(path, task, "metric.csv")) as f:
                 last = f.read().strip().splitlines()[-1].split(",")
             for k, v in zip(("PSNR", "SSIM", "LPIPS"), last[1:4]):
                 sums[k] += float(v) * n
+    if items == 0:
+        raise ValueError(f"merge_metrics: no time_consuming[.rank*].json with items under {path}")
     out = {"PSNR": float("inf"), "SSIM": 1.0, "LPIPS": 0.0} if vanilla else {k: v / items for k, v in sums.items()}
     out.update(Prompts=items, Latency=latency / items)
     with open(os.path.join(path, "merged_metric.txt"), "w") as f:

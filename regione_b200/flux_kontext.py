@@ -23,6 +23,13 @@ from .params import GAMMA, SCALAR_ROUNDS_TO_BF16
 from .schedule import calculate_shift, retrieve_timesteps
 
 gamma = GAMMA["FluxKontextPipeline"]          # inplace.py:47-50
+
+LATENT_SPACE_ONLY = (
+    "regione_b200: the patched pipeline of this family is LATENT-SPACE ONLY - it replaces the denoising loop and the "
+    "transformer forward, not the image processor / text encoders / VAE. Call it with packed `latents`, `image_latents` "
+    "and prompt embeds and `output_type='latent'`, encoding and decoding with the un-patched pipeline's own methods; "
+    "only the FluxKontext variant wires the host pipeline's encode_prompt / prepare_latents / VAE decode "
+    "(pipe(image=..., prompt=...)).")
 MANAGER = RegionManager()                     # inplace.py:51 (module-global singleton, one pipeline per process)
 
 

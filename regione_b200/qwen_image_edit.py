@@ -19,7 +19,7 @@ import torch
 from . import ops
 from .engine import cached_engine
 from .engine_qwen import QwenEngine
-from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
+from .flux_kontext import LATENT_SPACE_ONLY, RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
 
@@ -78,8 +78,8 @@ class RegionEQwenImageEditPipelineMixin:
                  output_type="pil", return_dict=True, attention_kwargs=None, image_latents=None,
                  condition_height=None, condition_width=None, **unused):
         assert num_inference_steps == MANAGER.inference_step, "num_inference_steps should be equal to 28"
-        if image_latents is None or latents is None or prompt_embeds is None:
-            raise RuntimeError("this pipeline has no encoders/VAE: pass latents, image_latents and prompt embeds")
+        if image_latents is None or latents is None or prompt_embeds is None or output_type != "latent":
+            raise NotImplementedError(LATENT_SPACE_ONLY)
         if height is None or width is None:
             raise ValueError("height and width are required with packed latents")
         device = self._execution_device
@@ -102,8 +102,6 @@ class RegionEQwenImageEditPipelineMixin:
                         else negative_prompt_embeds_mask.sum(dim=1).tolist())
         out = self.regione_denoise(latents, image_latents, prompt_embeds, negative_prompt_embeds if do_true_cfg else None,
                                    true_cfg_scale, img_shapes, txt_lens, neg_lens, height, width)
-        if output_type != "latent":
-            raise RuntimeError("this pipeline has no VAE: use output_type='latent'")
         if not return_dict:
             return (out,)
         return types.SimpleNamespace(images=out)

@@ -22,7 +22,7 @@ from . import _lib, ops
 from ._lib import G as GS
 from ._lib import check, ptr, stream_ptr
 from .engine import FluxEngine, cached_engine
-from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
+from .flux_kontext import LATENT_SPACE_ONLY, RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
 
@@ -126,8 +126,8 @@ class RegionEStep1XEditPipelineMixin:
                  joint_attention_kwargs=None, image_latents=None, timesteps_truncate=0.93, process_norm_power=0.4,
                  **unused):
         assert num_inference_steps == MANAGER.inference_step, "num_inference_steps should be equal to 28"
-        if image_latents is None or latents is None or prompt_embeds is None:
-            raise RuntimeError("this pipeline has no encoders/VAE: pass latents, image_latents and prompt embeds")
+        if image_latents is None or latents is None or prompt_embeds is None or output_type != "latent":
+            raise NotImplementedError(LATENT_SPACE_ONLY)
         if height is None or width is None:
             raise ValueError("height and width are required with packed latents")
         from .standin import latent_image_ids
@@ -151,8 +151,6 @@ class RegionEStep1XEditPipelineMixin:
         out = self.regione_denoise(latents, image_latents, latent_ids, text_ids, prompt_embeds, prompt_embeds_mask,
                                    negative_prompt_embeds if do_true_cfg else None, negative_prompt_embeds_mask,
                                    true_cfg_scale, timesteps_truncate, process_norm_power, height, width)
-        if output_type != "latent":
-            raise RuntimeError("this pipeline has no VAE: use output_type='latent'")
         if not return_dict:
             return (out,)
         return types.SimpleNamespace(images=out)

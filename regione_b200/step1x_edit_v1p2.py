@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .flux_kontext import RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
+from .flux_kontext import LATENT_SPACE_ONLY, RegionEB200AttnProcessor, RegionESchedulerMixin, calculate_shift, retrieve_timesteps
 from .manager import RegionManager, plan_steps
 from .params import GAMMA
 from .engine import cached_engine
@@ -74,8 +74,9 @@ class RegionEStep1XEditV1P2PipelineMixin:
                  joint_attention_kwargs=None, image_latents=None, timesteps_truncate=0.93, process_norm_power=0.4,
                  **unused):
         assert num_inference_steps == MANAGER.inference_step, "num_inference_steps should be equal to 28"
-        if image_latents is None or latents is None or prompt_embeds is None or negative_prompt_embeds is None:
-            raise RuntimeError("pass latents, image_latents, prompt_embeds and negative_prompt_embeds")
+        if (image_latents is None or latents is None or prompt_embeds is None or negative_prompt_embeds is None
+                or output_type != "latent"):
+            raise NotImplementedError(LATENT_SPACE_ONLY)
         if height is None or width is None:
             raise ValueError("height and width are required with packed latents")
         from .standin import latent_image_ids
@@ -93,8 +94,6 @@ class RegionEStep1XEditV1P2PipelineMixin:
         self.scheduler._step_index = 0
         out = self.regione_denoise(latents, image_latents, latent_ids, prompt_embeds, negative_prompt_embeds,
                                    true_cfg_scale, timesteps_truncate, process_norm_power, height, width)
-        if output_type != "latent":
-            raise RuntimeError("this pipeline has no VAE: use output_type='latent'")
         if not return_dict:
             return (out,)
         return types.SimpleNamespace(images=out)

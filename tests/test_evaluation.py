@@ -66,3 +66,21 @@ def test_folder_metrics_csv_and_merge(tmp_path):
     assert base["PSNR"] == float("inf") and base["SSIM"] == 1.0 and base["Latency"] == pytest.approx(2.0)
     txt = open(tmp_path / "RegionE" / "merged_metric.txt").read()
     assert [l.split(":")[0] for l in txt.strip().splitlines()] == ["PSNR", "SSIM", "LPIPS", "Prompts", "Latency"]
+
+
+def test_merge_metrics_recombines_rank_shards(tmp_path):
+    """A data-parallel evaluation (torchrun, regione_b200.cli) writes time_consuming.rank<r>.json per rank: the merge
+    sums the shards (and ignores a stale single-process file next to them); an empty directory is an error, not a
+    ZeroDivisionError."""
+    task = tmp_path / "pretrain" / "color_alter"
+    os.makedirs(task)
+    for r, (n, t) in enumerate(((3, 2.0), (1, 4.0))):
+        with open(task / f"time_consuming.rank{r}.json", "w") as f:
+            json.dump({"num_item": n, "ave_time_consuming": t, "time_consuming_list": [t] * n}, f)
+    with open(task / "time_consuming.json", "w") as f:          # stale file of an earlier single-process run
+        json.dump({"num_item": 100, "ave_time_consuming": 9.0, "time_consuming_list": []}, f)
+    merged = ev.merge_metrics(str(tmp_path / "pretrain"))
+    assert merged["Prompts"] == 4 and merged["Latency"] == pytest.approx((3 * 2.0 + 1 * 4.0) / 4)
+    os.makedirs(tmp_path / "empty" / "task")
+    with pytest.raises(ValueError):
+        ev.merge_metrics(str(tmp_path / "empty"))
