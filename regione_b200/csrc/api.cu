@@ -106,6 +106,38 @@ int device_sms() {
   return sms[dev];
 }
 
+// Stream-K workspace of the kernel-level entry points (rge_op_gemm[_group] with the gemm3 knob on): one per device,
+// allocated on first use. Callers of those entry points must not run two such launches concurrently on one device.
+struct StreamKWs { float* ws = nullptr; int* flags = nullptr; };
+StreamKWs* default_streamk_ws() {
+  static StreamKWs slots[kMaxDevices];
+  StreamKWs& w = slots[current_device()];
+  if (!w.ws) {
+    const int sms = device_sms();
+    if (cudaMalloc((void**)&w.ws, streamk_workspace_bytes(sms)) != cudaSuccess) { w.ws = nullptr; return &w; }
+    if (cudaMalloc((void**)&w.flags, streamk_flag_bytes(sms)) != cudaSuccess) {
+      cudaFree(w.ws); w.ws = nullptr; w.flags = nullptr; return &w;
+    }
+    cudaMemset(w.flags, 0, streamk_flag_bytes(sms));
+  }
+  return &w;
+}
+
+// gemm3 (tuning().gemm3 >= 1) when every member fits its envelope; `ws` may be null (no tile cuts)
+cudaError_t launch_group_auto(const GemmArgs* a, int n, int num_sms, float* ws, int* flags, cudaStream_t st) {
+  if (tuning().gemm3 > 0) {
+    bool ok = true;
+    for (int i = 0; i < n; ++i)
+      if (a[i].M > 0 && a[i].N > 0 && !(streamk_eligible(a[i]) && gemm_args_valid(a[i]))) ok = false;
+    if (ok) {
+      const bool cut = tuning().gemm3 >= 2 && ws && flags;
+      cudaError_t e = launch_gemm_streamk(a, n, num_sms, cut ? ws : nullptr, cut ? flags : nullptr, st);
+      if (e != cudaErrorNotSupported) return e;
+    }
+  }
+  return launch_gemm_group(a, n, num_sms, st);
+}
+
 GemmArgs to_args(const rge_gemm_desc* d) {
   GemmArgs a;
   a.A = (const bf16*)d->A; a.lda = d->lda;
@@ -194,7 +226,13 @@ int rge_op_gemm(const rge_gemm_desc* d, void* stream) {
   if (d->epilogue < 0 || d->epilogue > 3) return fail(RGE_ERR_INVALID, "rge_op_gemm: bad epilogue %d", d->epilogue);
   if (d->epilogue == RGE_EPI_NORM_ROPE && (!d->norm_w || !d->rope_cs))
     return fail(RGE_ERR_INVALID, "rge_op_gemm: NORM_ROPE needs norm_w and rope_cs");
-  RGE_LAUNCH(launch_gemm(to_args(d), device_sms(), (cudaStream_t)stream));
+  const GemmArgs a = to_args(d);
+  if (tuning().gemm3 > 0) {
+    StreamKWs* w = default_streamk_ws();
+    RGE_LAUNCH(launch_group_auto(&a, 1, device_sms(), w->ws, w->flags, (cudaStream_t)stream));
+    return RGE_OK;
+  }
+  RGE_LAUNCH(launch_gemm(a, device_sms(), (cudaStream_t)stream));
   return RGE_OK;
 }
 
@@ -206,7 +244,8 @@ int rge_op_gemm_group(const rge_gemm_desc* descs, int32_t n, void* stream) {
       return fail(RGE_ERR_INVALID, "rge_op_gemm_group: null operand in member %d", i);
     a[i] = to_args(&descs[i]);
   }
-  RGE_LAUNCH(launch_gemm_group(a, n, device_sms(), (cudaStream_t)stream));
+  StreamKWs* w = tuning().gemm3 > 0 ? default_streamk_ws() : nullptr;
+  RGE_LAUNCH(launch_group_auto(a, n, device_sms(), w ? w->ws : nullptr, w ? w->flags : nullptr, (cudaStream_t)stream));
   return RGE_OK;
 }
 
@@ -362,6 +401,15 @@ struct rge_handle {
   // the pre-attention stage gets faster (119 vs 184 us) but the free-running image / text chains after attention,
   // which overlap with the next block in the fan-out, are serialised at every stage.
   bool grouped = false;
+  // stream-K workspaces (gemm3.cu), one per stream the engine launches GEMMs on: [0] the caller's stream, [1..5] aux,
+  // [6] sattn - a region is never shared by two launches in flight
+  float* sk_ws[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* sk_flags = nullptr;     // 7 regions of num_sms ints
+  int sk_region(cudaStream_t s) const {
+    for (int i = 0; i < 5; ++i)
+      if (s == aux[i]) return 1 + i;
+    return s == sattn ? 6 : 0;
+  }
   // RGE_GROUP_QKV=1: keep the fan-out but launch the q / k / v projections of one stream (image, text, single block)
   // as one grouped launch on that stream's chain: fewer launch + prologue + un-overlapped-epilogue costs (5 - 15 us
   // each at REGION sizes, profiles/r01_prof_gemm1cta_region_summary.csv) without serialising independent chains.
@@ -382,6 +430,8 @@ cudaError_t dalloc(T** p, size_t count) {
   return cudaMalloc((void**)p, count * sizeof(T));
 }
 
+int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_cap = 0);
+
 int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bias, int N,
          int epi, bf16* out, long ldo, const int* row_map, int row_off, int col_off, const bf16* gate = nullptr,
          const bf16* res = nullptr, long ldr = 0, const bf16* norm_w = nullptr, const float2* rope = nullptr,
@@ -392,9 +442,7 @@ int gemm(rge_handle* h, cudaStream_t st, const bf16* A, long lda, int M, int K, 
   a.gate = gate; a.res = res; a.ldr = ldr; a.norm_w = norm_w; a.rope_cs = rope; a.rope_map = rope_map;
   a.rope_off = rope_off;
   if (M <= 0) return RGE_OK;
-  ProfScope prof(st, PC_GEMM, 2.0 * M * (double)N * K, M, N, K);
-  RGE_LAUNCH(launch_gemm(a, sm_cap > 0 ? sm_cap : h->num_sms, st));
-  return RGE_OK;
+  return gemm_group(h, st, &a, 1, sm_cap);
 }
 
 GemmArgs mk(const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bias, int N, int epi, bf16* out, long ldo,
@@ -409,13 +457,18 @@ GemmArgs mk(const bf16* A, long lda, int M, int K, const bf16* W, const bf16* bi
   return a;
 }
 
-int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_cap = 0) {
+int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_cap) {
   double work = 0;
   for (int i = 0; i < n; ++i)
     if (a[i].M > 0) work += 2.0 * a[i].M * (double)a[i].N * a[i].K;
   if (work == 0) return RGE_OK;
   ProfScope prof(st, PC_GEMM, work, a[0].M, n == 1 ? a[0].N : -n, a[0].K);   // N < 0: a group of |N| members
-  RGE_LAUNCH(launch_gemm_group(a, n, sm_cap > 0 ? sm_cap : h->num_sms, st));
+  // a launch capped to a few SMs runs BESIDE another kernel (attention tail fill): its CTA pairs are not all resident
+  // together, so its tiles stay whole (no stream-K cuts)
+  const int region = h->sk_region(st);
+  float* ws = sm_cap > 0 ? nullptr : h->sk_ws[region];
+  int* flags = h->sk_flags ? h->sk_flags + (size_t)region * h->num_sms : nullptr;
+  RGE_LAUNCH(launch_group_auto(a, n, sm_cap > 0 ? sm_cap : h->num_sms, ws, flags, st));
   return RGE_OK;
 }
 
@@ -807,6 +860,8 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   A(dalloc(&h->sel_img, S));
   A(dalloc(&h->sel_all, S));
   A(dalloc(&h->jobs, (size_t)2 + h->n_mod + 4 * cfg->n_pass));
+  for (int i = 0; i < 7; ++i) A(cudaMalloc((void**)&h->sk_ws[i], streamk_workspace_bytes(h->num_sms)));
+  A(dalloc(&h->sk_flags, (size_t)7 * h->num_sms));
   for (int i = 0; i < 5; ++i) {
     A(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&h->ev_aux[i], cudaEventDisableTiming));
@@ -829,6 +884,7 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
     return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));
   }
   // the cache must never expose uninitialised rows to attention
+  cudaMemset(h->sk_flags, 0, (size_t)7 * h->num_sms * sizeof(int));
   cudaMemset(h->kcache, 0, (size_t)cfg->n_pass * h->n_layers * S * D * sizeof(bf16));
   cudaMemset(h->vcache, 0, (size_t)cfg->n_pass * h->n_layers * S * D * sizeof(bf16));
   RGE_CUDA(cudaDeviceSynchronize());
@@ -839,7 +895,8 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
 int rge_destroy(rge_handle* h) {
   if (!h) return RGE_OK;
   void* ptrs[] = {h->h, h->n, h->q, h->big, h->kcache, h->vcache, h->mods, h->small, h->ctx, h->pass_small,
-                  h->rope, h->ids, h->sel_img, h->sel_all, h->jobs};
+                  h->rope, h->ids, h->sel_img, h->sel_all, h->jobs, h->sk_flags, h->sk_ws[0], h->sk_ws[1], h->sk_ws[2],
+                  h->sk_ws[3], h->sk_ws[4], h->sk_ws[5], h->sk_ws[6]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 5; ++i) {
@@ -1033,7 +1090,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   // A step whose widest GEMM (T + M rows) stays below the CTA-pair kernel's threshold is a REGION step (or a small
   // model): with RGE_GROUPED=1 every stage of a block is then ONE grouped launch on `st`. Otherwise the independent
   // GEMMs of a stage fan out over the side streams (the default: see rge_handle::grouped).
-  const bool grouped = h->grouped && r.MA < 2048;
+  const bool grouped = (h->grouped && r.MA < 2048) || tuning().gemm3 > 0;
   if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(st, h->ev_main, r.sT));
   // the last block of the stack computes only the rows whose output survives (bit-identical; tuning().trim_last)
   const bool trim = tuning().trim_last && h->fanout && !grouped && n_out < MA;

@@ -460,6 +460,8 @@ cudaError_t launch_gemm_group(const GemmArgs* args, int n, int num_sms, cudaStre
   return cudaGetLastError();
 }
 
+bool gemm_args_valid(const GemmArgs& a) { return gemm_args_ok(a); }
+
 void* get_tensor_map_encoder() { return reinterpret_cast<void*>(tensor_map_encoder()); }
 
 cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {

@@ -22,6 +22,9 @@ struct Tuning {
   int gemm_bn;       // RGE_GEMM_BN:     forced tile width of the 1-CTA GEMM, 0 = choose per launch
   int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never
   int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
+  int gemm3;         // RGE_GEMM3:       grouped stream-K CTA-pair GEMM (gemm3.cu): 0 = off, 1 = grouped launches with
+                     //                  whole-tile ranges (bit-identical to single launches), 2 = + stream-K tile cuts
+  int streamk;       // RGE_STREAMK:     0 = never cut tiles even where a workspace is available
   int trim_last;     // RGE_TRIM_LAST:   1 = the last block computes only the rows whose output is kept (default)
   int nvtx;          // RGE_NVTX:        1 = NVTX ranges per step / block / stage (profilers only)
 };
@@ -40,6 +43,8 @@ inline Tuning& tuning() {
     x.min_m_2cta = env_int("RGE_2CTA_MIN_M", 2048);
     const char* r = getenv("RGE_RASTER");
     x.raster = !r ? -1 : (r[0] == 'n' ? 1 : (r[0] == 'm' ? 0 : -1));
+    x.gemm3 = env_int("RGE_GEMM3", 0);
+    x.streamk = env_int("RGE_STREAMK", 1);
     x.trim_last = env_int("RGE_TRIM_LAST", 1);
     x.nvtx = env_int("RGE_NVTX", 0);
     return x;
@@ -55,6 +60,8 @@ inline bool set_tuning(const char* name, int value) {
   else if (!strcmp(name, "gemm_bn")) t.gemm_bn = value;
   else if (!strcmp(name, "2cta_min_m")) t.min_m_2cta = value;
   else if (!strcmp(name, "raster")) t.raster = value;
+  else if (!strcmp(name, "gemm3")) t.gemm3 = value;
+  else if (!strcmp(name, "streamk")) t.streamk = value;
   else if (!strcmp(name, "trim_last")) t.trim_last = value;
   else if (!strcmp(name, "nvtx")) t.nvtx = value;
   else return false;

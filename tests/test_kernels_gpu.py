@@ -447,3 +447,111 @@ def test_gemm_group_equals_single_launches():
     assert rel_l2(got[2][sel.long()], F.linear(x_img, wv, bv)) <= BF16_TOL
     assert rel_l2(got[3][:, D:], F.gelu(F.linear(x_img, wm, bm), approximate="tanh")) <= BF16_TOL
     assert rel_l2(got[4], res0 + gate[None] * F.linear(hid, wdown, bdown)) <= BF16_TOL
+
+
+def _ulp(a, b):
+    def key(x):
+        i = x.view(torch.int16).to(torch.int32)
+        return torch.where(i < 0, -(i & 0x7FFF), i)
+    return (key(a) - key(b)).abs()
+
+
+def test_gemm3_grouped_cta_pair_kernel_bit_identical_with_whole_tiles():
+    """gemm3.cu with `gemm3 = 1`: up to 6 GEMMs as one persistent CTA-pair launch over whole 256 x 256 tiles. Same
+    MMA shape and K order as the CTA-pair kernel, so every epilogue must be BIT-IDENTICAL to the members launched one by
+    one on it (2cta_min_m = 1 forces that kernel for the small members)."""
+    from regione_b200 import _lib, ops
+    g = _gen(61)
+    D, Dm, S, T, M = 512, 1024, 2600, 200, 1064
+
+    def lin(n, k):
+        return ((torch.randn(n, k, device="cuda", generator=g) * 0.05).bfloat16(),
+                torch.randn(n, device="cuda", generator=g).bfloat16())
+
+    x_img = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    x_txt = torch.randn(T, D, device="cuda", generator=g).bfloat16()
+    sel = (torch.randperm(S - T, device="cuda", generator=g)[:M].sort().values + T).int()
+    nw = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
+    cs = torch.randn(S, 64, 2, device="cuda", generator=g)
+    (wq, bq), (wk, bk), (wv, bv), (wm, bm) = lin(D, D), lin(D, D), lin(D, D), lin(Dm, D)
+    (wtq, btq), (wdown, bdown) = lin(D, D), lin(D, Dm)
+    gate = torch.randn(D, device="cuda", generator=g).bfloat16()
+    hid = torch.randn(M, Dm, device="cuda", generator=g).bfloat16()
+    res0 = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+
+    def members(q, kc, vc, big, res):
+        return [
+            (x_img, wq, bq, dict(epilogue=_lib.EPI_NORM_ROPE, out=q, row_off=T, norm_w=nw, rope_cs=cs, rope_map=sel)),
+            (x_img, wk, bk, dict(epilogue=_lib.EPI_NORM_ROPE, out=kc, row_map=sel, norm_w=nw, rope_cs=cs, rope_map=sel)),
+            (x_img, wv, bv, dict(out=vc, row_map=sel)),
+            (x_txt, wtq, btq, dict(epilogue=_lib.EPI_NORM_ROPE, out=q, norm_w=nw, rope_cs=cs)),
+            (x_img, wm, bm, dict(epilogue=_lib.EPI_GELU, out=big, col_off=D)),
+            (hid, wdown, bdown, dict(epilogue=_lib.EPI_GATE_RES, out=res, gate=gate, res=res)),
+        ]
+
+    def buffers():
+        return (torch.zeros(T + M, D, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(S, D, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(S, D, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(M, D + Dm, device="cuda", dtype=torch.bfloat16), res0.clone())
+
+    try:
+        ops.set_option("2cta_min_m", 1)
+        ref = buffers()
+        for a, w, b, kw in members(*ref):
+            ops.gemm(a, w, b, **kw)
+        ops.set_option("gemm3", 1)
+        got = buffers()
+        ops.gemm_group(members(*got))
+        torch.cuda.synchronize()
+        for r, o in zip(ref, got):
+            assert torch.equal(r, o)
+        # stream-K cuts (gemm3 = 2): fp32 partial sums are added in pair order - deterministic, and within one bf16
+        # ulp of the whole-tile result on (almost) every element
+        ops.set_option("gemm3", 2)
+        runs = []
+        for _ in range(2):
+            cut = buffers()
+            ops.gemm_group(members(*cut))
+            torch.cuda.synchronize()
+            runs.append(cut)
+        for a, b in zip(*runs):
+            assert torch.equal(a, b), "stream-K result changed between two launches"
+        for r, o in zip(ref, runs[0]):
+            d = _ulp(r, o)
+            assert int(d.max()) <= 2 and float((d == 0).float().mean()) > 0.97
+    finally:
+        ops.set_option("gemm3", 0)
+        ops.set_option("2cta_min_m", 2048)
+    assert rel_l2(got[2][sel.long()], F.linear(x_img, wv, bv)) <= BF16_TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 3072, 3072), (1064, 3072, 3072), (1576, 12288, 3072), (1576, 3072, 15360),
+                                   (8704, 3072, 3072), (300, 256, 4096)])
+def test_gemm3_streamk_cut_tiles_match_linear(M, N, K):
+    """Shapes of the hot path whose tile count is far from a multiple of the 74 SM pairs: every pair streams the same
+    number of k-blocks, cut tiles are fixed up from fp32 partials. Plain store and the in-place gate-residual epilogue,
+    launched twice (the workspace flags must re-arm)."""
+    from regione_b200 import _lib, ops
+    g = _gen(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.03).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    gate = torch.randn(N, device="cuda", generator=g).bfloat16()
+    res0 = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    want = F.linear(a.float(), w.float(), b.float())
+    try:
+        ops.set_option("gemm3", 2)
+        outs = []
+        for _ in range(2):
+            out = ops.gemm(a, w, b)
+            res = res0.clone()
+            ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, out=res, gate=gate, res=res)
+            torch.cuda.synchronize()
+            outs.append((out, res))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    finally:
+        ops.set_option("gemm3", 0)
+    assert rel_l2(outs[0][0], want) <= 3e-3
+    ref = res0.float() + (gate.float()[None] * want.bfloat16().float()).bfloat16().float()
+    assert rel_l2(outs[0][1], ref) <= 4e-3
