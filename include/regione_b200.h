@@ -166,6 +166,10 @@ typedef struct rge_config {
                              bit 1: temb is computed by the family's own modules and handed to rge_dit_step_ex
                              (Step1X: time_embed + vec_embed); RGE_G_TIME1..POOL2 stay unset.
                              pooled_dim = 0 drops the pooled-text term of temb (Qwen). */
+  int32_t shared_cache;   /* 1: every pass reads and writes ONE K/V cache set (FLUX true-CFG: the reference's processor
+                             owns a single k_cache / v_cache that both the prompt and the negative-prompt forward patch,
+                             RegionE/FluxKontext/inplace.py:349-364, :700-749); 0: one cache set per pass (Qwen /
+                             Step1X: k_cache_even / _odd, batch rows) */
 } rge_config;
 
 enum rge_block_kind { RGE_BLK_GLOBAL = 0, RGE_BLK_DOUBLE = 1, RGE_BLK_SINGLE = 2 };

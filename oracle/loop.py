@@ -68,8 +68,12 @@ def scheduler_step(sch: EulerState, st: ro.RegionState, model_output, sample, tr
 
 
 def run_regione(model, params: dict, gamma, latents, image_latents, latent_ids, text_ids, prompt_embeds, pooled,
-                guidance_scale: float, height: int, width: int, record: bool = False):
-    """inplace.py:287-392 for output_type='latent'. Returns (final latents [1,L,64], trace dict)."""
+                guidance_scale: float, height: int, width: int, record: bool = False, negative=None):
+    """inplace.py:287-392 for output_type='latent'. Returns (final latents [1,L,64], trace dict).
+    negative = (negative_prompt_embeds, negative_pooled_prompt_embeds, true_cfg_scale): the second forward of true-CFG
+    (:349-364). The model's processors own ONE k/v cache (:700-702), so both forwards patch and read the same cache -
+    the negative forward runs second and its rows are what a later REGION step of the prompt forward finds for the
+    unedited / instruction tokens."""
     st = ro.RegionState()
     st.set_parameters(params)
     n_steps = params["num_inference_steps"]
@@ -109,6 +113,10 @@ def run_regione(model, params: dict, gamma, latents, image_latents, latent_ids, 
             timestep = t.expand(latents.shape[0]).to(latents.dtype)                      # :334 (bf16-rounded)
             noise_pred = model.forward(st, x_in, prompt_embeds, pooled, timestep / 1000, latent_ids, text_ids,
                                        guidance)[:, : latents.size(1)]                   # :336-347
+            if negative is not None:                                                     # :349-364
+                neg = model.forward(st, x_in, negative[0], negative[1], timestep / 1000, latent_ids, text_ids,
+                                    guidance)[:, : latents.size(1)]
+                noise_pred = neg + negative[2] * (noise_pred - neg)
             cache = noise_pred                                                           # :365
             trace["modes"].append("FULL" if full else "REGION")
         latents = scheduler_step(sch, st, noise_pred, latents, trace)                    # :369

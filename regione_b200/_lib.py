@@ -76,7 +76,7 @@ class AttnDesc(C.Structure):
 class Config(C.Structure):
     _fields_ = [(n, c_int32) for n in (
         "dim", "heads", "n_double", "n_single", "mlp_ratio", "in_channels", "ctx_dim", "pooled_dim",
-        "txt_len", "lat_len", "cond_len", "guidance_embeds", "n_pass", "device", "external_embed")]
+        "txt_len", "lat_len", "cond_len", "guidance_embeds", "n_pass", "device", "external_embed", "shared_cache")]
 
 
 # name -> (restype, argtypes); every name here must be declared in include/regione_b200.h (tests check both ways)

@@ -418,8 +418,9 @@ struct rge_handle {
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
   const bf16* Sw(int b, int slot) const { return (const bf16*)sw[(size_t)b * RGE_S_NUM_SLOTS + slot]; }
-  bf16* kc(int pass, int layer) const { return kcache + ((size_t)pass * n_layers + layer) * (size_t)S * D; }
-  bf16* vc(int pass, int layer) const { return vcache + ((size_t)pass * n_layers + layer) * (size_t)S * D; }
+  int cset(int pass) const { return cfg.shared_cache ? 0 : pass; }
+  bf16* kc(int pass, int layer) const { return kcache + ((size_t)cset(pass) * n_layers + layer) * (size_t)S * D; }
+  bf16* vc(int pass, int layer) const { return vcache + ((size_t)cset(pass) * n_layers + layer) * (size_t)S * D; }
   bf16* ps(int pass) const { return pass_small + (size_t)pass * pass_small_stride; }
 };
 
@@ -849,8 +850,9 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   A(dalloc(&h->n, S * D));
   A(dalloc(&h->q, S * D));
   A(dalloc(&h->big, S * (D + (size_t)h->Dm)));
-  A(dalloc(&h->kcache, (size_t)cfg->n_pass * h->n_layers * S * D));
-  A(dalloc(&h->vcache, (size_t)cfg->n_pass * h->n_layers * S * D));
+  const size_t n_sets = cfg->shared_cache ? 1 : cfg->n_pass;
+  A(dalloc(&h->kcache, n_sets * h->n_layers * S * D));
+  A(dalloc(&h->vcache, n_sets * h->n_layers * S * D));
   A(dalloc(&h->mods, mods_elems));
   A(dalloc(&h->small, 256 + 3 * D));
   A(dalloc(&h->ctx, (size_t)cfg->n_pass * h->T * D + 8));
@@ -885,8 +887,8 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   }
   // the cache must never expose uninitialised rows to attention
   cudaMemset(h->sk_flags, 0, (size_t)7 * h->num_sms * sizeof(int));
-  cudaMemset(h->kcache, 0, (size_t)cfg->n_pass * h->n_layers * S * D * sizeof(bf16));
-  cudaMemset(h->vcache, 0, (size_t)cfg->n_pass * h->n_layers * S * D * sizeof(bf16));
+  cudaMemset(h->kcache, 0, n_sets * h->n_layers * S * D * sizeof(bf16));
+  cudaMemset(h->vcache, 0, n_sets * h->n_layers * S * D * sizeof(bf16));
   RGE_CUDA(cudaDeviceSynchronize());
   *out = h;
   return RGE_OK;

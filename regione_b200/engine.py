@@ -28,7 +28,8 @@ def _w(t: torch.Tensor, name: str) -> torch.Tensor:
 class FluxEngine:
     """FLUX-style DiT (double + single stream blocks; also Step1X-Edit's block stack)."""
 
-    def __init__(self, transformer, txt_len: int, lat_len: int, cond_len: int, n_pass: int = 1):
+    def __init__(self, transformer, txt_len: int, lat_len: int, cond_len: int, n_pass: int = 1,
+                 shared_cache: bool = False):
         self.lib = _lib.load()
         tr = transformer
         blocks, singles = list(tr.transformer_blocks), list(tr.single_transformer_blocks)
@@ -42,7 +43,7 @@ class FluxEngine:
             in_channels=in_ch, ctx_dim=tr.context_embedder.weight.shape[1],
             pooled_dim=tte.text_embedder.linear_1.weight.shape[1], txt_len=txt_len, lat_len=lat_len,
             cond_len=cond_len, guidance_embeds=int(self.guidance_embeds), n_pass=n_pass,
-            device=tr.x_embedder.weight.device.index or 0)
+            device=tr.x_embedder.weight.device.index or 0, shared_cache=int(shared_cache))
         self.cfg = cfg
         self.key = (txt_len, lat_len, cond_len, n_pass)
         self.in_channels = in_ch

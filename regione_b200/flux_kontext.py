@@ -134,18 +134,21 @@ class RegionESchedulerMixin:
 
 # ---------------------------------------------------------------------------------------------- patched forward
 def _get_engine(transformer, T, L, C, n_pass=1) -> FluxEngine:
-    return cached_engine(transformer, (T, L, C, n_pass), lambda: FluxEngine(transformer, T, L, C, n_pass))
+    # n_pass = 2 is true-CFG: two text contexts over ONE K/V cache set, like the reference's single processor cache
+    return cached_engine(transformer, (T, L, C, n_pass),
+                         lambda: FluxEngine(transformer, T, L, C, n_pass, shared_cache=n_pass > 1))
 
 
 def RegionEFluxTransformer2DModelforward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None,
                                          timestep=None, img_ids=None, txt_ids=None, guidance=None,
                                          joint_attention_kwargs=None, controlnet_block_samples=None,
                                          controlnet_single_block_samples=None, return_dict=True,
-                                         controlnet_blocks_repeat=False, condition_latents=None):
+                                         controlnet_blocks_repeat=False, condition_latents=None, regione_pass=0):
     """Same signature as the reference's patched forward (inplace.py:413-427) plus `condition_latents`: on FULL steps
     the loop hands the instruction-image latent separately ([1,C,64]) and the library reads the two row ranges in
     place, instead of `torch.cat([latents, image_latents], dim=1)` (inplace.py:332; a concatenated `hidden_states` is
-    still accepted). Mode selection follows the processor's rule (inplace.py:717-732): all L+C image tokens present
+    still accepted), and `regione_pass` (1 = the negative-prompt forward of true-CFG, inplace.py:349-364: its own text
+    context, the SAME K/V cache). Mode selection follows the processor's rule (inplace.py:717-732): all L+C image tokens present
     -> FULL (cache rows of every token are rewritten); fewer -> REGION with selection = MANAGER.edited_ids."""
     if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
         raise NotImplementedError("regione_b200: ControlNet residuals are outside the hot path")
@@ -167,7 +170,7 @@ def RegionEFluxTransformer2DModelforward(self, hidden_states, encoder_hidden_sta
         if x_cond is not None or M.edited_ids is None or x.shape[0] != M.edited_ids.numel():
             raise RuntimeError("regione_b200: region step without a matching edited-token selection")
         sel, n_out = M.edited_ids, x.shape[0]
-    out = engine.step(x, sel, t_x1000, n_out, x_cond=x_cond)[None]
+    out = engine.step(x, sel, t_x1000, n_out, pass_id=int(regione_pass), x_cond=x_cond)[None]
     if not return_dict:
         return (out,)
     return types.SimpleNamespace(sample=out)
@@ -188,10 +191,12 @@ class RegionEFluxKontextPipelineMixin:
                  true_cfg_scale=1.0, **unused):
         assert num_inference_steps == MANAGER.inference_step, "num_inference_steps should be equal to 28"   # :112
         # arguments of the reference's __call__ that this path does not implement are rejected, not swallowed
-        has_neg_prompt = any(unused.get(k) is not None for k in ("negative_prompt", "negative_prompt_embeds"))   # :176
-        if true_cfg_scale > 1 and has_neg_prompt:                                                           # :180
-            raise NotImplementedError("regione_b200: true-CFG (a negative prompt with true_cfg_scale > 1) needs a "
-                                      "second forward per step; not wired for FluxKontext")
+        negative_prompt, negative_prompt_2 = unused.get("negative_prompt"), unused.get("negative_prompt_2")
+        negative_prompt_embeds = unused.get("negative_prompt_embeds")
+        negative_pooled_prompt_embeds = unused.get("negative_pooled_prompt_embeds")
+        has_neg_prompt = negative_prompt is not None or (                                                   # :176-178
+            negative_prompt_embeds is not None and negative_pooled_prompt_embeds is not None)
+        do_true_cfg = true_cfg_scale > 1 and has_neg_prompt                                                 # :180
         for k in ("ip_adapter_image", "ip_adapter_image_embeds", "negative_ip_adapter_image",
                   "negative_ip_adapter_image_embeds", "callback_on_step_end", "sigmas"):
             if unused.get(k) is not None:
@@ -232,6 +237,12 @@ class RegionEFluxKontextPipelineMixin:
                 prompt=prompt, prompt_2=prompt_2, prompt_embeds=prompt_embeds,
                 pooled_prompt_embeds=pooled_prompt_embeds, device=device, num_images_per_prompt=num_images_per_prompt,
                 max_sequence_length=max_sequence_length, lora_scale=None)
+            if do_true_cfg:                                                                       # :193-209
+                negative_prompt_embeds, negative_pooled_prompt_embeds, _ = self.encode_prompt(
+                    prompt=negative_prompt, prompt_2=negative_prompt_2, prompt_embeds=negative_prompt_embeds,
+                    pooled_prompt_embeds=negative_pooled_prompt_embeds, device=device,
+                    num_images_per_prompt=num_images_per_prompt, max_sequence_length=max_sequence_length,
+                    lora_scale=None)
             nch = self.transformer.config.in_channels // 4
             latents, image_latents, latent_ids, image_ids = self.prepare_latents(
                 image, 1, nch, height, width, prompt_embeds.dtype, device, generator, latents)
@@ -253,8 +264,9 @@ class RegionEFluxKontextPipelineMixin:
         retrieve_timesteps(self.scheduler, num_inference_steps, device, sigmas=sigmas, mu=mu)     # :238-244
         self.scheduler.set_begin_index(0)   # known start: spares _init_step_index's device lookup (:606-607)
         self.scheduler._step_index = 0
+        negative = (negative_prompt_embeds, negative_pooled_prompt_embeds, float(true_cfg_scale)) if do_true_cfg else None
         latents = self.regione_denoise(latents, image_latents, latent_ids, text_ids, prompt_embeds,
-                                       pooled_prompt_embeds, guidance_scale, height, width)
+                                       pooled_prompt_embeds, guidance_scale, height, width, negative=negative)
         if output_type == "latent":
             image = latents
         else:
@@ -266,8 +278,9 @@ class RegionEFluxKontextPipelineMixin:
         return types.SimpleNamespace(images=image)
 
     def regione_denoise(self, latents, image_latents, latent_ids, text_ids, prompt_embeds, pooled_prompt_embeds,
-                        guidance_scale, height, width):
-        """The hot loop, inplace.py:287-392."""
+                        guidance_scale, height, width, negative=None):
+        """The hot loop, inplace.py:287-392. `negative` = (negative_prompt_embeds, negative_pooled_prompt_embeds,
+        true_cfg_scale) enables the second forward of true-CFG (:349-364)."""
         M = MANAGER
         N = M.inference_step
         sch = self.scheduler
@@ -275,11 +288,16 @@ class RegionEFluxKontextPipelineMixin:
         x = latents[0]
         cond = image_latents[0]
         L, C, T = x.shape[0], cond.shape[0], text_ids.shape[0]
-        engine = _get_engine(self.transformer, T, L, C)
+        if negative is not None and negative[0].shape[1] != T:
+            raise NotImplementedError("regione_b200: prompt and negative prompt must be padded to one length "
+                                      "(encode_prompt pads both to max_sequence_length)")
+        engine = _get_engine(self.transformer, T, L, C, n_pass=2 if negative is not None else 1)
         self.transformer.__dict__["_regione_b200_engine"] = engine
         M.refresh(x, cond, latent_ids, text_ids, 2, self.vae_scale_factor, height, width)          # :287
         g_x1000 = float(torch.tensor(guidance_scale, dtype=torch.float32).to(x.dtype) * 1000)     # :250, :473
         engine.begin_image(text_ids, latent_ids, prompt_embeds[0], pooled_prompt_embeds[0], g_x1000)
+        if negative is not None:
+            engine.begin_image(text_ids, latent_ids, negative[0][0], negative[1][0], g_x1000, pass_id=1)
         guidance = torch.full([1], guidance_scale, dtype=torch.float32)
         plan = plan_steps(ts_host, gamma, M)                                                      # :295-313
         cache = None
@@ -308,6 +326,13 @@ class RegionEFluxKontextPipelineMixin:
                                               img_ids=latent_ids, joint_attention_kwargs=None, return_dict=False,
                                               condition_latents=image_latents if full else None)[0]   # :331-332
                 noise_pred = noise_pred[0, : x.shape[0]]                                          # :347
+                if negative is not None:                                                          # :349-364
+                    neg = self.transformer(hidden_states=x[None], timestep=timestep / 1000, guidance=guidance,
+                                           pooled_projections=negative[1], encoder_hidden_states=negative[0],
+                                           txt_ids=text_ids, img_ids=latent_ids, joint_attention_kwargs=None,
+                                           return_dict=False, condition_latents=image_latents if full else None,
+                                           regione_pass=1)[0][0, : x.shape[0]]
+                    noise_pred = ops.cfg_combine(noise_pred, neg, negative[2])   # neg + scale * (pos - neg), :364
                 cache = noise_pred                                                                # :365
                 x = sch.step(noise_pred, t, x, return_dict=False)[0]                               # :369
                 self.regione_trace["modes"].append("FULL" if full else "REGION")
