@@ -250,6 +250,10 @@ def run_ours(args):
         mine = {"rank": rank, "schedule": "".join(m[0] for m in modes), "edited_tokens": n_edited}
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
+        # the NCCL mask all-gather of the last image (side stream, step warmup-1) must describe the same partitions
+        from_masks = fk.MANAGER.batch_edited_counts()
+        assert from_masks == [g_["edited_tokens"] for g_ in gathered], \
+            f"gathered partition masks {from_masks} disagree with the ranks' own counts {gathered}"
         host0 = syn.make_inputs(110, grid, grid, txt, arch["ctx_dim"], arch["pooled_dim"], rho=args.rho)
         out0 = pipe(guidance_scale=2.5, num_inference_steps=28, output_type="latent", return_dict=False,
                     **{k: host0[k].to(dev) for k in keys}, **hw)[0]
@@ -261,7 +265,8 @@ def run_ours(args):
         all_digests = [torch.zeros_like(digest) for _ in range(world)]
         dist.all_gather(all_digests, digest)
         identical = all(torch.equal(d, all_digests[0]) for d in all_digests)
-        replica = {"per_rank": gathered, "seed_110_edited_tokens": int(all_digests[0][2]),
+        replica = {"per_rank": gathered, "edited_tokens_from_gathered_masks": from_masks,
+                   "seed_110_edited_tokens": int(all_digests[0][2]),
                    "seed_110_bit_identical_across_ranks": bool(identical),
                    "same_schedule_on_all_ranks": len({g["schedule"] for g in gathered}) == 1}
         assert identical, "replicas disagree on the same input: " + str([d.tolist() for d in all_digests])

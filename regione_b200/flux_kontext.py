@@ -44,14 +44,63 @@ def enable_mask_allgather(on: bool = True) -> None:
     _MASK_ALLGATHER = bool(on)
 
 
-def allgather_masks(raw_mask: torch.Tensor):
-    """[L] uint8 per rank -> [world, L] on every rank (no-op without an initialised process group)."""
+def _world() -> int:
     import torch.distributed as dist
-    if not (_MASK_ALLGATHER and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-        return raw_mask[None]
-    out = torch.empty(dist.get_world_size() * raw_mask.numel(), dtype=raw_mask.dtype, device=raw_mask.device)
-    dist.all_gather_into_tensor(out, raw_mask.contiguous())
-    return out.view(dist.get_world_size(), raw_mask.numel())
+    if not (_MASK_ALLGATHER and dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size()
+
+
+def allgather_masks(mask: torch.Tensor):
+    """[L] uint8 per rank -> [world, L] on every rank (no-op without an initialised process group). Blocking form."""
+    import torch.distributed as dist
+    if _world() == 1:
+        return mask[None]
+    out = torch.empty(dist.get_world_size() * mask.numel(), dtype=mask.dtype, device=mask.device)
+    dist.all_gather_into_tensor(out, mask.contiguous())
+    return out.view(dist.get_world_size(), mask.numel())
+
+
+class PendingMasks:
+    """The [world, L] batch mask while its all-gather is still in flight on a side stream. `get()` makes the CURRENT
+    stream wait for the collective (no host block) and returns the tensor."""
+
+    def __init__(self, out, work, side):
+        self.out, self.work, self.side = out, work, side
+
+    def get(self):
+        if self.work is not None:
+            self.work.wait()
+            if self.side is not None:
+                torch.cuda.current_stream().wait_stream(self.side)
+            self.work = None
+        return self.out
+
+
+_SIDE_STREAM = {}
+
+
+def allgather_masks_async(mask: torch.Tensor) -> PendingMasks:
+    """Starts the all-gather of this rank's [L] partition mask on a side stream ordered after the work already queued
+    on the current stream (the kernel that produced the mask), so that the collective overlaps the two-speed Euler
+    update and the host's wait for the token counts. CPU tensors (gloo, tests) gather asynchronously too."""
+    import torch.distributed as dist
+    if _world() == 1:
+        return PendingMasks(mask[None], None, None)
+    world = dist.get_world_size()
+    out = torch.empty(world * mask.numel(), dtype=mask.dtype, device=mask.device)
+    if not mask.is_cuda:
+        work = dist.all_gather_into_tensor(out, mask.contiguous(), async_op=True)
+        return PendingMasks(out.view(world, mask.numel()), work, None)
+    side = _SIDE_STREAM.get(mask.device)
+    if side is None:
+        side = _SIDE_STREAM[mask.device] = torch.cuda.Stream(device=mask.device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        work = dist.all_gather_into_tensor(out, mask.contiguous(), async_op=True)
+    mask.record_stream(side)
+    out.record_stream(side)
+    return PendingMasks(out.view(world, mask.numel()), work, side)
 
 
 def _scalar(s: torch.Tensor) -> float:
@@ -114,12 +163,19 @@ class RegionESchedulerMixin:
             raw = ops.partition(x, v, M.condition_latent.reshape(-1, ch), _scalar(dt_final), float(M.threshold))
             gh = M.height // (M.patch_size * M.vae_scale_factor)
             gw = M.width // (M.patch_size * M.vae_scale_factor)
-            M.batch_masks = allgather_masks(raw)       # [world, L]; this rank's image is row `rank`
-            if M.batch_masks.shape[0] > 1:
-                import torch.distributed as dist
-                raw = M.batch_masks[dist.get_rank()]
-            M.edited_mask, M.edited_ids, M.unedited_ids = ops.compact(raw, gh, gw, bool(M.erosion_dilation))
-            prev = ops.euler(x, v, _scalar(dt), _scalar(dt_direct), edited_mask=M.edited_mask)
+            box = {}
+
+            def after_mask(final_mask):
+                # needs the mask but not the token counts: enqueued BEFORE the host waits for the counts. The
+                # all-gather of the partition (one image per rank -> the [world, L] batch partition, the path's only
+                # collective) runs on a side stream beside the Euler update.
+                box["prev"] = ops.euler(x, v, _scalar(dt), _scalar(dt_direct), edited_mask=final_mask)
+                box["masks"] = allgather_masks_async(final_mask)
+
+            M.edited_mask, M.edited_ids, M.unedited_ids = ops.compact(raw, gh, gw, bool(M.erosion_dilation),
+                                                                      before_sync=after_mask)
+            M.batch_masks_pending = box["masks"]       # [world, L] once `M.batch_masks` is read
+            prev = box["prev"]
         elif M.prev_refresh_step is not None and M.current_step == M.prev_refresh_step:          # :665-677
             prev = ops.euler(x, v, _scalar(dt), _scalar(dt_direct) if dt_direct is not None else 0.0,
                              edited_mask=M.edited_mask)

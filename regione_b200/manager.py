@@ -43,6 +43,19 @@ class RegionManager:
         self.next_refresh_step = None
         self.refresh_step_real_time = []
 
+    @property
+    def batch_masks(self):
+        """[world, L] uint8: the partition (after morphology) of every image of the data-parallel batch, one image per
+        rank, all-gathered at step warmup-1 (flux_kontext.allgather_masks_async); this rank's image is row `rank`.
+        Reading it orders the current stream after the collective. None before the partition step."""
+        p = getattr(self, "batch_masks_pending", None)
+        return None if p is None else p.get()
+
+    def batch_edited_counts(self):
+        """Edited tokens of every image of the batch (host list; one small device->host read)."""
+        m = self.batch_masks
+        return None if m is None else [int(c) for c in m.sum(dim=1).tolist()]
+
     def set_parameters(self, args) -> None:
         """utils.py:390-402, same validation and the same appended sentinel."""
         user_gamma = args.get("gamma")   # extension: a caller-supplied table lifts the 28-step restriction
@@ -77,6 +90,7 @@ class RegionManager:
         self.prev_refresh_step = None
         self.next_refresh_step = None
         self.edited_ids = self.unedited_ids = self.edited_mask = None
+        self.batch_masks_pending = None
         self.unedited_latent = None
         self.latent_ids = latent_ids
         self.refresh_step_real_time = list(self.refresh_step)

@@ -227,9 +227,17 @@ def partition(x, v, cond, dt_final: float, threshold: float, want_sim: bool = Fa
     return (mask, sim) if want_sim else mask
 
 
-def compact(mask, grid_h: int, grid_w: int, erosion_dilation: bool):
-    """-> (final mask uint8 [L], edited_ids int32 [n_e], unedited_ids int32 [L-n_e]); one D2H sync for the counts
-    (the reference syncs at the same point through boolean indexing, utils.py:347)."""
+_PINNED_COUNTS = {}
+
+
+def compact(mask, grid_h: int, grid_w: int, erosion_dilation: bool, before_sync=None):
+    """-> (final mask uint8 [L], edited_ids int32 [n_e], unedited_ids int32 [L-n_e]).
+
+    One host synchronisation for the two counts (the reference syncs at the same point through boolean indexing,
+    utils.py:347). It is the ONLY sync of an image, and it is taken late: the counts travel through an asynchronous
+    copy into pinned host memory followed by an event; `before_sync(final_mask)` - the caller's chance to enqueue
+    everything that needs the mask but not the counts (two-speed Euler update, mask all-gather) - runs first, and only
+    then does the host wait on the event."""
     lib = _lib.load()
     _req(mask, torch.uint8, "mask")
     L = grid_h * grid_w
@@ -240,5 +248,14 @@ def compact(mask, grid_h: int, grid_w: int, erosion_dilation: bool):
     counts = torch.empty(2, dtype=torch.int32, device=dev)
     check(lib.rge_compact(ptr(mask), ptr(out_mask), grid_h, grid_w, 1 if erosion_dilation else 0, ptr(edited),
                           ptr(unedited), ptr(counts), stream_ptr()), "rge_compact")
-    n_e = int(counts[0].item())
+    host = _PINNED_COUNTS.get(dev)
+    if host is None:
+        host = _PINNED_COUNTS[dev] = torch.empty(2, dtype=torch.int32).pin_memory()
+    host.copy_(counts, non_blocking=True)
+    done = torch.cuda.Event()
+    done.record()
+    if before_sync is not None:
+        before_sync(out_mask)
+    done.synchronize()
+    n_e = int(host[0])
     return out_mask, edited[:n_e], unedited[: L - n_e]

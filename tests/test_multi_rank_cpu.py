@@ -31,6 +31,12 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
             gr = torch.Generator().manual_seed(100 + r)
             expect = (torch.rand(L, generator=gr) < 0.25 + 0.25 * r).to(torch.uint8)
             assert torch.equal(allm[r], expect), f"rank {rank}: row {r} of the gathered mask is wrong"
+        # the asynchronous form the scheduler step uses (side stream on CUDA; async work on gloo) + the manager's view
+        pend = fk.allgather_masks_async(raw)
+        mm = RegionManager()
+        mm.batch_masks_pending = pend
+        assert torch.equal(mm.batch_masks, allm) and mm.batch_masks is mm.batch_masks
+        assert mm.batch_edited_counts() == [int(allm[r].sum()) for r in range(world)]
         # planner decisions depend only on the schedule -> identical on every rank
         m = RegionManager()
         m.set_parameters(dict(params.DEFAULTS["FluxKontextPipeline"], threshold=0.88))

@@ -14,7 +14,9 @@ Two epilogues:
   * direct fp32 -> bf16 (what the engine stores): differs from the Triton result only where the double rounding bites
     - an fp16 value whose three dropped mantissa bits are exactly 100b is a tie for the second rounding (1 in 8), which
     ties-to-even resolves against the sign of the first rounding's error half of the time: ~6 % of the elements, each
-    by one bf16 ulp. Gate: >= 92 % bit-identical, at most one ulp.
+    by one bf16 ulp. Gate: >= 92 % bit-identical; at most one ulp wherever the value is a NORMAL fp16 number
+    (|x| >= 2^-14); below that fp16 is subnormal (absolute spacing 2^-24), where the Triton result carries an absolute
+    error of up to 2^-25 that spans several bf16 ulps of such tiny values - bounded absolutely there.
 Rows outside the index must stay untouched by both kernels (bit-exact)."""
 import pytest
 import torch
@@ -70,9 +72,11 @@ def test_scatter_gemm_matches_the_reference_triton_kernel(M, S_cache, single):
     d16, d = ulp_diff(x16, r), ulp_diff(x, r)
     same16, same = float((d16 == 0).float().mean()), float((d == 0).float().mean())
     print(f"M={M} S={S_cache}: fp16-roundtrip epilogue bit-identical to Triton on {100 * same16:.3f} % (max {int(d16.max())} ulp); "
-          f"direct fp32->bf16 epilogue on {100 * same:.3f} % (max {int(d.max())} ulp)")
+          f"direct fp32->bf16 epilogue on {100 * same:.3f} % (max {int(d.max())} ulp, fp16-subnormal values included)")
     assert int(d16.max()) <= 1 and same16 >= 0.995
-    assert int(d.max()) <= 1 and same >= 0.92
+    normal = r.float().abs() >= 2.0 ** -14
+    assert same >= 0.92 and int(d[normal].max()) <= 1
+    assert float((x.float() - r.float())[~normal].abs().max()) <= 2.0 ** -24 if bool((~normal).any()) else True
     # and both are the same linear map as torch (fp32 reference of the op)
     want = (a[0].float() @ w.float().t() + b.float())
     assert float((x.float() - want).norm() / want.norm()) < 3e-3

@@ -58,6 +58,15 @@ def main():
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=pos)
             fns["ours_norm_rope(pair-major table)"] = lambda: ops.gemm(
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_map=pos, rope_ld=S)
+        if N % 256 == 0:                     # gemm3.cu: CTA-pair tiles, stream-K ranges (and whole-tile ranges)
+            def sk(mode):
+                def run():
+                    ops.set_option("gemm3", mode)
+                    ops.gemm(a, w, b, out=out)
+                    ops.set_option("gemm3", 0)
+                return run
+            fns["gemm3 stream-K"] = sk(2)
+            fns["gemm3 whole tiles"] = sk(1)
         if M < 2048 and N % 256 == 0:        # the CTA-pair kernel below its default row threshold
             def pair():
                 ops.set_option("2cta_min_m", 1)
@@ -74,6 +83,45 @@ def main():
             time.sleep(0.2)
         print(f"M={M} N={N} K={K}: " + "  |  ".join(
             f"{k} {v[0]:.0f}/{v[1]:.0f}" for k, v in res.items()) + "   (burst/sustained TF/s)", flush=True)
+    # ---- the q / k / v (+ text q / k / v) projections of one double block as ONE launch (gemm3) vs six launches
+    D, S = 3072, 8704
+    nw = torch.ones(128, device="cuda").bfloat16()
+    cs_pm = torch.randn(64, S, 2, device="cuda")
+    for M_img, T in ((8192, 512), (1064, 512), (360, 512), (4608, 256)):
+        xi = torch.randn(M_img, D, device="cuda").bfloat16()
+        xt = torch.randn(T, D, device="cuda").bfloat16()
+        ws = [(torch.randn(D, D, device="cuda") * 0.02).bfloat16() for _ in range(6)]
+        bs = [torch.randn(D, device="cuda").bfloat16() for _ in range(6)]
+        q = torch.empty(T + M_img, D, device="cuda", dtype=torch.bfloat16)
+        kc = torch.empty(S, D, device="cuda", dtype=torch.bfloat16)
+        vc = torch.empty(S, D, device="cuda", dtype=torch.bfloat16)
+        pos = torch.arange(M_img, device="cuda", dtype=torch.int32)
+        nr = dict(epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_ld=S)
+        members = [(xi, ws[0], bs[0], dict(out=q, row_off=T, rope_map=pos, rope_off=T, **nr)),
+                   (xi, ws[1], bs[1], dict(out=kc, row_map=pos, row_off=T, rope_map=pos, rope_off=T, **nr)),
+                   (xi, ws[2], bs[2], dict(out=vc, row_map=pos, row_off=T)),
+                   (xt, ws[3], bs[3], dict(out=q, **nr)), (xt, ws[4], bs[4], dict(out=kc, **nr)),
+                   (xt, ws[5], bs[5], dict(out=vc))]
+        fl = 2.0 * (M_img + T) * D * D * 3
+
+        def six():
+            for a_, w_, b_, kw in members:
+                ops.gemm(a_, w_, b_, **kw)
+
+        def grouped(mode):
+            def run():
+                ops.set_option("gemm3", mode)
+                ops.gemm_group(members)
+                ops.set_option("gemm3", 0)
+            return run
+        r = {}
+        for name, fn in (("six launches (one stream)", six), ("1-CTA grouped kernel", lambda: ops.gemm_group(members)),
+                         ("gemm3 whole tiles", grouped(1)), ("gemm3 stream-K", grouped(2))):
+            for _ in range(3):
+                fn()
+            r[name] = timeit(fn, secs)
+        print(f"q/k/v + text q/k/v, image rows {M_img}, text rows {T}: " + "  |  ".join(
+            f"{k} {v * 1e3:.1f} us {fl / v / 1e9:.0f} TF/s" for k, v in r.items()), flush=True)
     # ---- scatter-GEMM vs the reference's Triton kernel at its call sites (inplace.py:734-747)
     try:
         from oracle.build_ref import load_partially_linear
