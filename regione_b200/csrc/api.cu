@@ -106,32 +106,14 @@ int device_sms() {
   return sms[dev];
 }
 
-// Stream-K workspace of the kernel-level entry points (rge_op_gemm[_group] with the gemm3 knob on): one per device,
-// allocated on first use. Callers of those entry points must not run two such launches concurrently on one device.
-struct StreamKWs { float* ws = nullptr; int* flags = nullptr; };
-StreamKWs* default_streamk_ws() {
-  static StreamKWs slots[kMaxDevices];
-  StreamKWs& w = slots[current_device()];
-  if (!w.ws) {
-    const int sms = device_sms();
-    if (cudaMalloc((void**)&w.ws, streamk_workspace_bytes(sms)) != cudaSuccess) { w.ws = nullptr; return &w; }
-    if (cudaMalloc((void**)&w.flags, streamk_flag_bytes(sms)) != cudaSuccess) {
-      cudaFree(w.ws); w.ws = nullptr; w.flags = nullptr; return &w;
-    }
-    cudaMemset(w.flags, 0, streamk_flag_bytes(sms));
-  }
-  return &w;
-}
-
-// gemm3 (tuning().gemm3 >= 1) when every member fits its envelope; `ws` may be null (no tile cuts)
-cudaError_t launch_group_auto(const GemmArgs* a, int n, int num_sms, float* ws, int* flags, cudaStream_t st) {
+// grouped CTA-pair kernel (tuning().gemm3) when every member fits its envelope, else the grouped 1-CTA kernel
+cudaError_t launch_group_auto(const GemmArgs* a, int n, int num_sms, cudaStream_t st) {
   if (tuning().gemm3 > 0) {
     bool ok = true;
     for (int i = 0; i < n; ++i)
-      if (a[i].M > 0 && a[i].N > 0 && !(streamk_eligible(a[i]) && gemm_args_valid(a[i]))) ok = false;
+      if (a[i].M > 0 && a[i].N > 0 && !(group2_eligible(a[i]) && gemm_args_valid(a[i]))) ok = false;
     if (ok) {
-      const bool cut = tuning().gemm3 >= 2 && ws && flags;
-      cudaError_t e = launch_gemm_streamk(a, n, num_sms, cut ? ws : nullptr, cut ? flags : nullptr, st);
+      cudaError_t e = launch_gemm_group2(a, n, num_sms, st);
       if (e != cudaErrorNotSupported) return e;
     }
   }
@@ -227,11 +209,6 @@ int rge_op_gemm(const rge_gemm_desc* d, void* stream) {
   if (d->epilogue == RGE_EPI_NORM_ROPE && (!d->norm_w || !d->rope_cs))
     return fail(RGE_ERR_INVALID, "rge_op_gemm: NORM_ROPE needs norm_w and rope_cs");
   const GemmArgs a = to_args(d);
-  if (tuning().gemm3 > 0) {
-    StreamKWs* w = default_streamk_ws();
-    RGE_LAUNCH(launch_group_auto(&a, 1, device_sms(), w->ws, w->flags, (cudaStream_t)stream));
-    return RGE_OK;
-  }
   RGE_LAUNCH(launch_gemm(a, device_sms(), (cudaStream_t)stream));
   return RGE_OK;
 }
@@ -244,8 +221,7 @@ int rge_op_gemm_group(const rge_gemm_desc* descs, int32_t n, void* stream) {
       return fail(RGE_ERR_INVALID, "rge_op_gemm_group: null operand in member %d", i);
     a[i] = to_args(&descs[i]);
   }
-  StreamKWs* w = tuning().gemm3 > 0 ? default_streamk_ws() : nullptr;
-  RGE_LAUNCH(launch_group_auto(a, n, device_sms(), w ? w->ws : nullptr, w ? w->flags : nullptr, (cudaStream_t)stream));
+  RGE_LAUNCH(launch_group_auto(a, n, device_sms(), (cudaStream_t)stream));
   return RGE_OK;
 }
 
@@ -401,19 +377,10 @@ struct rge_handle {
   // the pre-attention stage gets faster (119 vs 184 us) but the free-running image / text chains after attention,
   // which overlap with the next block in the fan-out, are serialised at every stage.
   bool grouped = false;
-  // stream-K workspaces (gemm3.cu), one per stream the engine launches GEMMs on: [0] the caller's stream, [1..5] aux,
-  // [6] sattn - a region is never shared by two launches in flight
-  float* sk_ws[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int* sk_flags = nullptr;     // 7 regions of num_sms ints
-  int sk_region(cudaStream_t s) const {
-    for (int i = 0; i < 5; ++i)
-      if (s == aux[i]) return 1 + i;
-    return s == sattn ? 6 : 0;
-  }
   // RGE_GROUP_QKV=1: keep the fan-out but launch the q / k / v projections of one stream (image, text, single block)
   // as one grouped launch on that stream's chain: fewer launch + prologue + un-overlapped-epilogue costs (5 - 15 us
   // each at REGION sizes, profiles/r01_prof_gemm1cta_region_summary.csv) without serialising independent chains.
-  bool group_qkv = false;
+  int group_qkv = 0;    // 1: q / k / v of one stream as one launch; 2: image AND text q / k / v of a double block as one
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
@@ -464,12 +431,8 @@ int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_
     if (a[i].M > 0) work += 2.0 * a[i].M * (double)a[i].N * a[i].K;
   if (work == 0) return RGE_OK;
   ProfScope prof(st, PC_GEMM, work, a[0].M, n == 1 ? a[0].N : -n, a[0].K);   // N < 0: a group of |N| members
-  // a launch capped to a few SMs runs BESIDE another kernel (attention tail fill): its CTA pairs are not all resident
-  // together, so its tiles stay whole (no stream-K cuts)
-  const int region = h->sk_region(st);
-  float* ws = sm_cap > 0 ? nullptr : h->sk_ws[region];
-  int* flags = h->sk_flags ? h->sk_flags + (size_t)region * h->num_sms : nullptr;
-  RGE_LAUNCH(launch_group_auto(a, n, sm_cap > 0 ? sm_cap : h->num_sms, ws, flags, st));
+  if (n == 1) RGE_LAUNCH(launch_gemm(a[0], sm_cap > 0 ? sm_cap : h->num_sms, st));
+  else RGE_LAUNCH(launch_group_auto(a, n, sm_cap > 0 ? sm_cap : h->num_sms, st));
   return RGE_OK;
 }
 
@@ -601,7 +564,7 @@ struct StepRun {
   }
   int one(cudaStream_t s, const GemmArgs& a, int sm_cap = 0) const { return gemm_group(h, s, &a, 1, sm_cap); }
   // grouped q / k / v only where the members take the 1-CTA path anyway (REGION-sized steps, text stream)
-  bool group_qkv() const { return h->group_qkv && h->fanout && MA < 2048; }
+  int group_qkv() const { return h->fanout && (MA < 2048 || tuning().gemm3 > 0) ? h->group_qkv : 0; }
 
   // adaLN vectors of a double block: image stream at mod, text stream at mod + 6 D; each shift, scale, gate x 2
   int double_block_fanout(int b, int layer, const bf16* mod) const {
@@ -611,7 +574,12 @@ struct StepRun {
     bf16* vc = h->vc(pass, layer);
     // image chain on `st`, text chain on sT, joined around attention
     RGE_LAUNCH(launch_ln_modulate(x_img, D, mod + D, mod, n_img_p, D, M, D, st));
-    if (group_qkv()) {
+    if (group_qkv() >= 2) {   // all six projections of the block in ONE launch on `st` (the text LayerNorm joins first)
+      RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
+      RGE_CUDA(link(sT, h->ev_txt, st));
+      const GemmArgs qkv[6] = {img_q(b), img_k(b, kc), img_v(b, vc), txt_q(b), txt_k(b, kc), txt_v(b, vc)};
+      RGE_TRY(gemm_group(h, st, qkv, 6));
+    } else if (group_qkv()) {
       const GemmArgs iq[3] = {img_q(b), img_k(b, kc), img_v(b, vc)};
       RGE_TRY(gemm_group(h, st, iq, 3));
       RGE_LAUNCH(launch_ln_modulate(h->h, D, cm + D, cm, h->n, D, T, D, sT));
@@ -862,8 +830,6 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   A(dalloc(&h->sel_img, S));
   A(dalloc(&h->sel_all, S));
   A(dalloc(&h->jobs, (size_t)2 + h->n_mod + 4 * cfg->n_pass));
-  for (int i = 0; i < 7; ++i) A(cudaMalloc((void**)&h->sk_ws[i], streamk_workspace_bytes(h->num_sms)));
-  A(dalloc(&h->sk_flags, (size_t)7 * h->num_sms));
   for (int i = 0; i < 5; ++i) {
     A(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&h->ev_aux[i], cudaEventDisableTiming));
@@ -880,13 +846,12 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
   if (const char* env = getenv("RGE_NO_FANOUT")) h->fanout = env[0] == '0' || env[0] == 0;
   if (const char* env = getenv("RGE_FILL_ATTN_TAIL")) h->fill_attn_tail = env[0] != '0';
   if (const char* env = getenv("RGE_GROUPED")) h->grouped = env[0] != '0';
-  if (const char* env = getenv("RGE_GROUP_QKV")) h->group_qkv = env[0] != '0';
+  if (const char* env = getenv("RGE_GROUP_QKV")) h->group_qkv = atoi(env);
   if (e != cudaSuccess) {
     rge_destroy(h);
     return fail(RGE_ERR_CUDA, "rge_create: allocation failed: %s", cudaGetErrorString(e));
   }
   // the cache must never expose uninitialised rows to attention
-  cudaMemset(h->sk_flags, 0, (size_t)7 * h->num_sms * sizeof(int));
   cudaMemset(h->kcache, 0, n_sets * h->n_layers * S * D * sizeof(bf16));
   cudaMemset(h->vcache, 0, n_sets * h->n_layers * S * D * sizeof(bf16));
   RGE_CUDA(cudaDeviceSynchronize());
@@ -897,8 +862,7 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
 int rge_destroy(rge_handle* h) {
   if (!h) return RGE_OK;
   void* ptrs[] = {h->h, h->n, h->q, h->big, h->kcache, h->vcache, h->mods, h->small, h->ctx, h->pass_small,
-                  h->rope, h->ids, h->sel_img, h->sel_all, h->jobs, h->sk_flags, h->sk_ws[0], h->sk_ws[1], h->sk_ws[2],
-                  h->sk_ws[3], h->sk_ws[4], h->sk_ws[5], h->sk_ws[6]};
+                  h->rope, h->ids, h->sel_img, h->sel_all, h->jobs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 5; ++i) {
@@ -1092,7 +1056,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   // A step whose widest GEMM (T + M rows) stays below the CTA-pair kernel's threshold is a REGION step (or a small
   // model): with RGE_GROUPED=1 every stage of a block is then ONE grouped launch on `st`. Otherwise the independent
   // GEMMs of a stage fan out over the side streams (the default: see rge_handle::grouped).
-  const bool grouped = (h->grouped && r.MA < 2048) || tuning().gemm3 > 0;
+  const bool grouped = h->grouped && (r.MA < 2048 || tuning().gemm3 > 0);
   if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(st, h->ev_main, r.sT));
   // the last block of the stack computes only the rows whose output survives (bit-identical; tuning().trim_last)
   const bool trim = tuning().trim_last && h->fanout && !grouped && n_out < MA;

@@ -1,22 +1,21 @@
-// Grouped stream-K variant of the CTA-pair (cluster of two, tcgen05 cta_group::2) bf16 GEMM: up to kMaxGroup
-// independent GEMMs - the q / k / v (/ text q / k / v) projections of a block, or the image- and text-stream halves of
-// one stage - as ONE persistent launch whose work is the concatenation of all members' (256 x 256 tile, 64-wide k-block)
-// units, cut into one contiguous, equally long range per CTA pair.
+// Grouped variant of the CTA-pair (cluster of two, tcgen05 cta_group::2) bf16 GEMM: up to kMaxGroup3 independent GEMMs -
+// the q / k / v (/ text q / k / v) projections of a block, or the image- and text-stream halves of one stage - as ONE
+// persistent launch whose tile list is the concatenation of all members' 256 x 256 tiles, cut into one contiguous,
+// equally long (in k-blocks) range of whole tiles per CTA pair.
 //
-// Why: the hot path's GEMMs rarely fill a whole number of waves of the 74 SM pairs (FULL step, N = K = 3072: 408 tiles
-// = 5.5 waves; REGION step, M ~ 1000-1600: 60-84 tiles = 0.8-1.1 waves; text stream, M = 512: 24 tiles = 0.3 waves),
-// and launched one by one the small ones are bound by the L2 -> shared-memory fill of 128-row tiles. Here every pair
-// streams the same number of k-blocks through 256 x 256 tiles; a tile whose k range is cut by a range boundary is
-// finished by the pair that holds its FIRST k-block (the "owner": it reaches the tile at the END of its range), which
-// adds the fp32 partial accumulators the following pair(s) left in a workspace at the START of their ranges - so nobody
-// waits for work that has not been issued yet (stream-K, Osama et al. 2023). With `split` off the ranges are snapped to
-// tile boundaries: plain grouped data-parallel launch, bit-identical to the members launched one by one.
+// Why: launched one by one, the hot path's GEMMs rarely fill a whole number of waves of the 74 SM pairs (REGION step,
+// M ~ 1000-1600: 60-84 tiles = 0.8-1.1 waves; text stream, M = 512: 24 tiles = 0.3 waves), and as 128-row tiles of the
+// 1-CTA kernel the small ones are bound by the L2 -> shared-memory fill. Same MMA shape, K order and epilogues as
+// gemm2.cu, so results are bit-identical to the members launched one by one on that kernel.
+//
+// A stream-K version of this kernel (ranges cutting tiles, fp32 partials fixed up through a global workspace) was
+// built and measured in round 2 (profiles/r02_gemm3_streamk_rejected.log): correct and deterministic, but the fix-up
+// - 128 KB of partial accumulator per CTA through L2 per cut, read back by the tile's owner - cost more than the wave
+// quantisation it removed on every shape of the path (e.g. 512 x 3072 x 3072: 168 vs 315 TFLOP/s), so it was removed.
 //
 //   warp 0      TMA producer (both CTAs; transaction bytes are credited to the leader's `full` barrier)
 //   warp 1      MMA issuer   (leader CTA only) / TMEM allocation (both CTAs, cta_group::2)
-//   warps 2-5   epilogue     (both CTAs): complete tile -> fused epilogue (gemm_epilogue.cuh); tile started elsewhere ->
-//               fp32 partial to the workspace + flag; owner of a cut tile -> wait for the flags, add the partials in
-//               pair order (deterministic), write the sum back to TMEM, fused epilogue
+//   warps 2-5   epilogue     (both CTAs; the member's epilogue is selected per tile)
 #include "gemm_epilogue.cuh"
 #include "tmap.cuh"
 
@@ -36,7 +35,7 @@ constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 constexpr int kTmemCols = 512;
 constexpr int kMaxGroup3 = 6;
 
-struct StreamKParams {
+struct Group2Params {
   CUtensorMap map_a[kMaxGroup3];
   CUtensorMap map_b[kMaxGroup3];
   GemmDev p[kMaxGroup3];
@@ -46,9 +45,6 @@ struct StreamKParams {
   int num_kb[kMaxGroup3];
   int epi[kMaxGroup3];
   int n_prob;
-  int split;                   // 1: ranges may cut tiles (stream-K); 0: snapped to tile boundaries
-  float* ws;                   // [pairs][2 CTAs][256 columns][128 rows] fp32 partial accumulators
-  int* flags;                  // [pairs][2 CTAs]: epilogue warps of the contributor that have published (0 .. 4)
 };
 
 struct Segment {
@@ -56,8 +52,8 @@ struct Segment {
   long tile_begin;             // unit index of the tile's first k-block
 };
 
-// unit -> (member, tile, k-block); snap == true moves u down to the first unit of its tile
-__device__ __forceinline__ Segment decode_unit(const StreamKParams& g, long u) {
+// unit -> (member, tile, k-block)
+__device__ __forceinline__ Segment decode_unit(const Group2Params& g, long u) {
   Segment s;
   s.prob = 0;
   long base = 0;
@@ -74,25 +70,14 @@ __device__ __forceinline__ Segment decode_unit(const StreamKParams& g, long u) {
   return s;
 }
 
-__device__ __forceinline__ long range_begin(const StreamKParams& g, long total, int pair, int num_pairs) {
-  long u = total * pair / num_pairs;
-  if (!g.split && u < total) u = decode_unit(g, u).tile_begin;
-  return u;
-}
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <int EPI>
-__device__ __noinline__ void epilogue_call(const GemmDev& p, uint32_t taddr, int m, int n_base) {
-  gemm_epilogue_row<EPI>(p, taddr, m, n_base, BN);
+// first unit of pair `pair`'s range: an equal share of the k-blocks, snapped down to a tile boundary
+__device__ __forceinline__ long range_begin(const Group2Params& g, long total, int pair, int num_pairs) {
+  const long u = total * pair / num_pairs;
+  return u < total ? decode_unit(g, u).tile_begin : u;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm3_kernel(const __grid_constant__ StreamKParams g) {
+gemm3_kernel(const __grid_constant__ Group2Params g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -142,9 +127,8 @@ gemm3_kernel(const __grid_constant__ StreamKParams g) {
       int stage = 0;
       uint32_t phase = 0;
       for (long u = u0; u < u1;) {
-        Segment s = decode_unit(g, u);
-        const long seg_end = min(u1, s.tile_begin + s.kb1);
-        s.kb1 = s.kb0 + (int)(seg_end - u);
+        const Segment s = decode_unit(g, u);
+        const long seg_end = s.tile_begin + s.kb1;
         const CUtensorMap* ma = &g.map_a[s.prob];
         const CUtensorMap* mb = &g.map_b[s.prob];
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
@@ -168,9 +152,8 @@ gemm3_kernel(const __grid_constant__ StreamKParams g) {
       uint32_t phase = 0;
       int it = 0;
       for (long u = u0; u < u1; ++it) {
-        Segment s = decode_unit(g, u);
-        const long seg_end = min(u1, s.tile_begin + s.kb1);
-        s.kb1 = s.kb0 + (int)(seg_end - u);
+        const Segment s = decode_unit(g, u);
+        const long seg_end = s.tile_begin + s.kb1;
         const int acc = it & 1;
         const uint32_t use = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], use ^ 1);
@@ -199,78 +182,26 @@ gemm3_kernel(const __grid_constant__ StreamKParams g) {
     const int r = q * 32 + lane;
     int it = 0;
     for (long u = u0; u < u1; ++it) {
-      Segment s = decode_unit(g, u);
-      const int nkb = s.kb1;
-      const long tile_end = s.tile_begin + nkb;
-      const long seg_end = min(u1, tile_end);
-      s.kb1 = s.kb0 + (int)(seg_end - u);
+      const Segment s = decode_unit(g, u);
       const int acc = it & 1;
       const uint32_t use = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      if (s.kb0 > 0) {
-        // ---- this tile was started by an earlier pair: leave the fp32 partial in this pair's workspace slot.
-        // Layout [column][row]: the 32 lanes (rows) of a warp write 128 contiguous bytes per column.
-        float* slot = g.ws + ((size_t)pair * 2 + rank) * (size_t)(BN * BM) + r;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) __stcg(slot + (size_t)(c * 32 + j) * BM, __uint_as_float(v[j]));
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(g.flags + pair * 2 + rank, 1);
-      } else {
-        if (s.kb1 < nkb) {
-          // ---- owner of a cut tile: the following pairs computed the rest of the k range at the START of their
-          // ranges; add their partials in pair order, write the sums back into the accumulator
-          for (int cq = pair + 1; cq < num_pairs; ++cq) {
-            if (range_begin(g, total, cq, num_pairs) >= tile_end) break;
-            const int* flag = g.flags + cq * 2 + rank;
-            if (lane == 0) {
-              long long t0 = clock64();
-              while (ld_acquire(flag) < 4) {
-                __nanosleep(64);
-                if (clock64() - t0 > RGE_WAIT_TIMEOUT_CYCLES) __trap();
-              }
-            }
-            __syncwarp();
-            const float* slot = g.ws + ((size_t)cq * 2 + rank) * (size_t)(BN * BM) + r;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld32(taddr + c * 32, v);
-              float part[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) part[j] = __ldcg(slot + (size_t)(c * 32 + j) * BM);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + part[j]);
-              tmem_st32(taddr + c * 32, v);
-            }
-            tmem_st_wait();
-            // all four epilogue warps of this CTA have consumed the slot: re-arm its flag for the next launch
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (r == 0) atomicExch(g.flags + cq * 2 + rank, 0);
-          }
-        }
-        const GemmDev& p = g.p[s.prob];
-        const int m = s.m_blk * 2 * BM + (int)rank * BM + r, n0 = s.n_blk * BN;
-        switch (g.epi[s.prob]) {
-          case EPI_STORE: epilogue_call<EPI_STORE>(p, taddr, m, n0); break;
-          case EPI_GELU: epilogue_call<EPI_GELU>(p, taddr, m, n0); break;
-          case EPI_GATE_RES: epilogue_call<EPI_GATE_RES>(p, taddr, m, n0); break;
-          default: epilogue_call<EPI_NORM_ROPE>(p, taddr, m, n0); break;
-        }
+      // the member's epilogue parameters BY VALUE: through a reference into the kernel-parameter block the compiler has
+      // to re-read every field after each global store (the stores may alias it) - measured 30 % slower
+      const GemmDev p = g.p[s.prob];
+      const int m = s.m_blk * 2 * BM + (int)rank * BM + r, n0 = s.n_blk * BN;
+      switch (g.epi[s.prob]) {
+        case EPI_STORE: gemm_epilogue_row<EPI_STORE>(p, taddr, m, n0, BN); break;
+        case EPI_GELU: gemm_epilogue_row<EPI_GELU>(p, taddr, m, n0, BN); break;
+        case EPI_GATE_RES: gemm_epilogue_row<EPI_GATE_RES>(p, taddr, m, n0, BN); break;
+        default: gemm_epilogue_row<EPI_NORM_ROPE>(p, taddr, m, n0, BN); break;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
-      u = seg_end;
+      u = s.tile_begin + s.kb1;
     }
   }
 
@@ -281,21 +212,17 @@ gemm3_kernel(const __grid_constant__ StreamKParams g) {
 
 }  // namespace
 
-size_t streamk_workspace_bytes(int num_sms) { return (size_t)(num_sms / 2) * 2 * BN * BM * sizeof(float); }
-size_t streamk_flag_bytes(int num_sms) { return (size_t)(num_sms / 2) * 2 * sizeof(int); }
-
-bool streamk_eligible(const GemmArgs& a) {
+bool group2_eligible(const GemmArgs& a) {
   return a.M > 0 && a.N > 0 && a.N % BN == 0 && a.K > 0 && a.K % 8 == 0;
 }
 
-// `ws` / `flags`: a workspace of streamk_workspace_bytes / streamk_flag_bytes (flags zero-initialised once) that no
-// other launch in flight uses - the engine keeps one per stream. ws == nullptr disables tile splitting.
-cudaError_t launch_gemm_streamk(const GemmArgs* args, int n, int num_sms, float* ws, int* flags, cudaStream_t stream) {
+// Returns cudaErrorNotSupported if a member is outside the envelope (nothing launched).
+cudaError_t launch_gemm_group2(const GemmArgs* args, int n, int num_sms, cudaStream_t stream) {
   const GemmArgs* live[kMaxGroup3];
   int n_live = 0;
   for (int i = 0; i < n; ++i) {
     if (args[i].M <= 0 || args[i].N <= 0) continue;
-    if (!streamk_eligible(args[i]) || n_live == kMaxGroup3) return cudaErrorNotSupported;
+    if (!group2_eligible(args[i]) || n_live == kMaxGroup3) return cudaErrorNotSupported;
     live[n_live++] = &args[i];
   }
   if (n_live == 0) return cudaSuccess;
@@ -306,14 +233,14 @@ cudaError_t launch_gemm_streamk(const GemmArgs* args, int n, int num_sms, float*
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  // members with the longest tiles (largest K) first: with splitting off, the short tiles even out the end
+  // members with the longest tiles (largest K) first, so that the short tiles even out the end of the launch
   int order[kMaxGroup3];
   for (int i = 0; i < n_live; ++i) order[i] = i;
   for (int i = 1; i < n_live; ++i)
     for (int j = i; j > 0 && live[order[j]]->K > live[order[j - 1]]->K; --j) {
       const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
     }
-  StreamKParams g;
+  Group2Params g;
   long units = 0, tiles = 0;
   for (int k = 0; k < n_live; ++k) {
     const GemmArgs& a = *live[order[k]];
@@ -331,13 +258,8 @@ cudaError_t launch_gemm_streamk(const GemmArgs* args, int n, int num_sms, float*
   }
   for (int k = n_live; k < kMaxGroup3; ++k) g.unit_end[k] = units;
   g.n_prob = n_live;
-  g.ws = ws;
-  g.flags = flags;
-  const int max_pairs = num_sms / 2;
-  g.split = ws != nullptr && flags != nullptr && tuning().streamk != 0;
-  // never cut a range shorter than ~8 k-blocks: the fix-up would cost more than the imbalance it removes
-  long pairs = g.split ? (units / 8 < max_pairs ? units / 8 : max_pairs) : (tiles < max_pairs ? tiles : max_pairs);
-  if (pairs < 1) pairs = 1;
+  const long max_pairs = num_sms / 2;
+  const long pairs = tiles < max_pairs ? tiles : max_pairs;
   gemm3_kernel<<<(unsigned)(2 * pairs), kThreads, kSmemBytes, stream>>>(g);
   return cudaGetLastError();
 }

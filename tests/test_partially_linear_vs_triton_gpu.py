@@ -16,7 +16,8 @@ Two epilogues:
     ties-to-even resolves against the sign of the first rounding's error half of the time: ~6 % of the elements, each
     by one bf16 ulp. Gate: >= 92 % bit-identical; at most one ulp wherever the value is a NORMAL fp16 number
     (|x| >= 2^-14); below that fp16 is subnormal (absolute spacing 2^-24), where the Triton result carries an absolute
-    error of up to 2^-25 that spans several bf16 ulps of such tiny values - bounded absolutely there.
+    error of up to 2^-25 that spans several bf16 ulps of such tiny values - bounded absolutely there (2^-22: the fp16
+    rounding plus the two bf16 roundings of values just under 2^-14).
 Rows outside the index must stay untouched by both kernels (bit-exact)."""
 import pytest
 import torch
@@ -76,7 +77,8 @@ def test_scatter_gemm_matches_the_reference_triton_kernel(M, S_cache, single):
     assert int(d16.max()) <= 1 and same16 >= 0.995
     normal = r.float().abs() >= 2.0 ** -14
     assert same >= 0.92 and int(d[normal].max()) <= 1
-    assert float((x.float() - r.float())[~normal].abs().max()) <= 2.0 ** -24 if bool((~normal).any()) else True
+    if bool((~normal).any()):
+        assert float((x.float() - r.float())[~normal].abs().max()) <= 2.0 ** -22
     # and both are the same linear map as torch (fp32 reference of the op)
     want = (a[0].float() @ w.float().t() + b.float())
     assert float((x.float() - want).norm() / want.norm()) < 3e-3

@@ -58,15 +58,12 @@ def main():
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=pos)
             fns["ours_norm_rope(pair-major table)"] = lambda: ops.gemm(
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_map=pos, rope_ld=S)
-        if N % 256 == 0:                     # gemm3.cu: CTA-pair tiles, stream-K ranges (and whole-tile ranges)
-            def sk(mode):
-                def run():
-                    ops.set_option("gemm3", mode)
-                    ops.gemm(a, w, b, out=out)
-                    ops.set_option("gemm3", 0)
-                return run
-            fns["gemm3 stream-K"] = sk(2)
-            fns["gemm3 whole tiles"] = sk(1)
+        if N % 256 == 0:                     # gemm3.cu: the grouped CTA-pair kernel with a single member
+            def g3():
+                ops.set_option("gemm3", 1)
+                ops.gemm_group([(a, w, b, dict(out=out))])
+                ops.set_option("gemm3", 0)
+            fns["gemm3 (1 member)"] = g3
         if M < 2048 and N % 256 == 0:        # the CTA-pair kernel below its default row threshold
             def pair():
                 ops.set_option("2cta_min_m", 1)
@@ -116,7 +113,7 @@ def main():
             return run
         r = {}
         for name, fn in (("six launches (one stream)", six), ("1-CTA grouped kernel", lambda: ops.gemm_group(members)),
-                         ("gemm3 whole tiles", grouped(1)), ("gemm3 stream-K", grouped(2))):
+                         ("gemm3 grouped CTA-pair kernel", grouped(1))):
             for _ in range(3):
                 fn()
             r[name] = timeit(fn, secs)

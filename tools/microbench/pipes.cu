@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256, 1) bench(int mode, long long* cycles, flo
     for (int it = 0; it < kIters; ++it) {
       tmem_ld32p(t, v); tmem_ld32p(t + 32, v + 32); tmem_ld32p(t + 64, v + 64); tmem_ld32p(t + 96, v + 96);
       tmem_ld_wait();
-      acc += __uint_as_float(v[it & 127]);
+      acc += __uint_as_float(v[0] ^ v[37] ^ v[64] ^ v[127]);   // static indices: v stays in registers
     }
   } else if (mode == 1) {
     for (int it = 0; it < kIters; ++it) {
