@@ -106,20 +106,6 @@ int device_sms() {
   return sms[dev];
 }
 
-// grouped CTA-pair kernel (tuning().gemm3) when every member fits its envelope, else the grouped 1-CTA kernel
-cudaError_t launch_group_auto(const GemmArgs* a, int n, int num_sms, cudaStream_t st) {
-  if (tuning().gemm3 > 0) {
-    bool ok = true;
-    for (int i = 0; i < n; ++i)
-      if (a[i].M > 0 && a[i].N > 0 && !(group2_eligible(a[i]) && gemm_args_valid(a[i]))) ok = false;
-    if (ok) {
-      cudaError_t e = launch_gemm_group2(a, n, num_sms, st);
-      if (e != cudaErrorNotSupported) return e;
-    }
-  }
-  return launch_gemm_group(a, n, num_sms, st);
-}
-
 GemmArgs to_args(const rge_gemm_desc* d) {
   GemmArgs a;
   a.A = (const bf16*)d->A; a.lda = d->lda;
@@ -221,7 +207,7 @@ int rge_op_gemm_group(const rge_gemm_desc* descs, int32_t n, void* stream) {
       return fail(RGE_ERR_INVALID, "rge_op_gemm_group: null operand in member %d", i);
     a[i] = to_args(&descs[i]);
   }
-  RGE_LAUNCH(launch_group_auto(a, n, device_sms(), (cudaStream_t)stream));
+  RGE_LAUNCH(launch_gemm_group(a, n, device_sms(), (cudaStream_t)stream));
   return RGE_OK;
 }
 
@@ -377,10 +363,12 @@ struct rge_handle {
   // the pre-attention stage gets faster (119 vs 184 us) but the free-running image / text chains after attention,
   // which overlap with the next block in the fan-out, are serialised at every stage.
   bool grouped = false;
-  // RGE_GROUP_QKV=1: keep the fan-out but launch the q / k / v projections of one stream (image, text, single block)
-  // as one grouped launch on that stream's chain: fewer launch + prologue + un-overlapped-epilogue costs (5 - 15 us
-  // each at REGION sizes, profiles/r01_prof_gemm1cta_region_summary.csv) without serialising independent chains.
-  int group_qkv = 0;    // 1: q / k / v of one stream as one launch; 2: image AND text q / k / v of a double block as one
+  // RGE_GROUP_QKV (default 1): keep the fan-out but, in REGION-sized steps, launch the q / k / v projections of one
+  // stream (image, text, single block) as ONE grouped launch on that stream's chain - fewer launch + prologue +
+  // un-overlapped-epilogue costs without serialising independent chains: 41.6 -> 39.4 ms per REGION step
+  // (profiles/r02_step_times_launch_variants.log); 2 = image AND text q / k / v of a double block as one launch (40.1 ms);
+  // 0 = one launch per projection
+  int group_qkv = 1;
 
   const bf16* G(int slot) const { return (const bf16*)gw[slot]; }
   const bf16* Dw(int b, int slot) const { return (const bf16*)dw[(size_t)b * RGE_D_NUM_SLOTS + slot]; }
@@ -432,7 +420,7 @@ int gemm_group(rge_handle* h, cudaStream_t st, const GemmArgs* a, int n, int sm_
   if (work == 0) return RGE_OK;
   ProfScope prof(st, PC_GEMM, work, a[0].M, n == 1 ? a[0].N : -n, a[0].K);   // N < 0: a group of |N| members
   if (n == 1) RGE_LAUNCH(launch_gemm(a[0], sm_cap > 0 ? sm_cap : h->num_sms, st));
-  else RGE_LAUNCH(launch_group_auto(a, n, sm_cap > 0 ? sm_cap : h->num_sms, st));
+  else RGE_LAUNCH(launch_gemm_group(a, n, sm_cap > 0 ? sm_cap : h->num_sms, st));
   return RGE_OK;
 }
 
@@ -564,7 +552,7 @@ struct StepRun {
   }
   int one(cudaStream_t s, const GemmArgs& a, int sm_cap = 0) const { return gemm_group(h, s, &a, 1, sm_cap); }
   // grouped q / k / v only where the members take the 1-CTA path anyway (REGION-sized steps, text stream)
-  int group_qkv() const { return h->fanout && (MA < 2048 || tuning().gemm3 > 0) ? h->group_qkv : 0; }
+  int group_qkv() const { return h->fanout && MA < 2048 ? h->group_qkv : 0; }
 
   // adaLN vectors of a double block: image stream at mod, text stream at mod + 6 D; each shift, scale, gate x 2
   int double_block_fanout(int b, int layer, const bf16* mod) const {
@@ -1056,7 +1044,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   // A step whose widest GEMM (T + M rows) stays below the CTA-pair kernel's threshold is a REGION step (or a small
   // model): with RGE_GROUPED=1 every stage of a block is then ONE grouped launch on `st`. Otherwise the independent
   // GEMMs of a stage fan out over the side streams (the default: see rge_handle::grouped).
-  const bool grouped = h->grouped && (r.MA < 2048 || tuning().gemm3 > 0);
+  const bool grouped = h->grouped && r.MA < 2048;
   if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(st, h->ev_main, r.sT));
   // the last block of the stack computes only the rows whose output survives (bit-identical; tuning().trim_last)
   const bool trim = tuning().trim_last && h->fanout && !grouped && n_out < MA;

@@ -11,12 +11,14 @@
 // the other's softmax runs. Online softmax uses a lazy reference maximum: O is only rescaled (by the softmax group
 // itself, in TMEM) when a row maximum grows by more than 2^8.
 //
-// The softmax leg is software-pipelined in two 64-column halves, because its three resources are each as slow as the
-// tensor pipe for one tile (TMEM read of the fp32 scores, 16 ex2 per clock, and the MMAs themselves): S = Q K^T is
-// issued and committed as two N = 64 halves, the softmax group pulls half 0 into registers as soon as it exists, has
-// half 1's TMEM loads in flight while it exponentiates half 0, publishes P half 0 (its four P V MMAs start), then
-// finishes half 1. The reference maximum is therefore decided per half: if half 1 raises it by more than 2^8, the group
-// waits for the P V MMAs of half 0 (committed on their own barrier), rescales O and the half-0 row sum, and goes on.
+// Measured and rejected in round 2 (profiles/r02_attn_bench_pipe_poly_variants.log, r02_ncu_attention_source_hotspots.txt):
+//   * evaluating 2-4 of every 8 exponential pairs as a packed-FFMA2 polynomial instead of MUFU.EX2 (kept as the
+//     `attn_poly` knob): 3-8 % slower at every shape although MUFU and tensor pipe are co-critical (63 % each) - the
+//     extra ~4 issue slots per offloaded score cost the single softmax warp per scheduler more than the MUFU time saves;
+//   * S = Q K^T and the softmax in two software-pipelined 64-column halves (own commit per half, half 1's TMEM loads in
+//     flight during half 0's exponentials): 17 % slower - TMEM reads are not a bottleneck (measured 720-920 B/clk/SM,
+//     profiles/r02_pipes_microbench.log) and the second barrier round trip per tile lengthens the serial
+//     S-ready -> softmax -> P-ready -> MMA chain that bounds this design (41 % of softmax-warp samples wait for S).
 //
 // Replaces flash_attn_func(q, k, v, causal=False) at RegionE/FluxKontext/inplace.py:796-801; K/V are read in place
 // from the Region-Instruction KV cache instead of being re-normalised, re-rotated and re-concatenated every step
@@ -39,7 +41,6 @@ constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kSlots = 5;
 constexpr int kSmemBytes = 2 * kTileBytes + kSlots * kTileBytes + 256 + 1024;
 constexpr int kDefaultPoly = 0;         // exponential pairs of every 8 on the FMA pipe (RGE_ATTN_POLY overrides)
-constexpr int kDefaultPipe = 0;         // software-pipelined score halves (RGE_ATTN_PIPE overrides)
 constexpr uint32_t kColS = 0, kColO = 256;  // TMEM column bases: S_i at kColS + 128 i, O_i at kColO + 128 i
 
 struct AttnDev {
@@ -87,7 +88,7 @@ __device__ __forceinline__ constexpr bool poly_pair(int kPoly, int pair) {
 }
 
 // kPoly = how many of every eight score PAIRS use ex2_poly2 instead of MUFU.EX2 (0, 2, 3 or 4).
-template <int kPoly, bool kPipe>
+template <int kPoly>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnDev p) {
@@ -99,11 +100,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + kSlots;
-  uint64_t* s_full = kv_empty + kSlots;   // [group][half]: score columns [64 half, 64 half + 64) are in TMEM
-  uint64_t* p_half = s_full + 4;          // [group][half]: P columns [64 half, 64 half + 64) of the group are in TMEM
-  uint64_t* o_bar = p_half + 4;           // [group]: every P V MMA of the tile has completed
-  uint64_t* o_half = o_bar + 2;           // [group]: the P V MMAs of half 0 of the tile have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_half + 2);
+  uint64_t* s_full = kv_empty + kSlots;
+  uint64_t* p_half = s_full + 2;   // [group][half]: P columns [64 half, 64 half + 64) of the group are in TMEM
+  uint64_t* o_bar = p_half + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,12 +121,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mbar_init(&kv_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[2 * i], 1);
-      mbar_init(&s_full[2 * i + 1], 1);
+      mbar_init(&s_full[i], 1);
       mbar_init(&p_half[2 * i], 4);
       mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&o_bar[i], 1);
-      mbar_init(&o_half[i], 1);
     }
     fence_mbar_init();
   }
@@ -164,7 +162,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, 0, 0);   // one 64-column half of S per MMA group
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
       const uint32_t sq_addr = smem_u32(s_q);
       const uint32_t skv_addr = smem_u32(s_kv);
@@ -173,30 +171,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         mbar_wait(&kv_full[t % kSlots], (t / kSlots) & 1);
         tc_fence_after();
       };
-      // S_i = Q_i K^T : contraction over d, 8 steps of 16; both operands K-major, 128B-swizzled. Two halves of 64 kv
-      // rows (8 KB apart in the K tile), each committed on its own barrier so the softmax group can start on half 0
+      // S_i = Q_i K^T : contraction over d, 8 steps of 16; both operands K-major, 128B-swizzled
       auto issue_qk = [&](int i, uint32_t k_addr) {
-        if constexpr (kPipe) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-              umma_ss(tmem + kColS + i * 128 + half * 64, make_sdesc_sw128(sq_addr + i * kTileBytes + off, 0, 1024),
-                      make_sdesc_sw128(k_addr + half * 8192 + off, 0, 1024), idesc_qk, kk != 0);
-            }
-            tc_commit(&s_full[2 * i + half]);
-          }
-        } else {   // one N = 128 MMA group, one commit (both halves of s_full complete together)
-          constexpr uint32_t idesc_qk128 = make_idesc_bf16(128, 128, 0, 0);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-            umma_ss(tmem + kColS + i * 128, make_sdesc_sw128(sq_addr + i * kTileBytes + off, 0, 1024),
-                    make_sdesc_sw128(k_addr + off, 0, 1024), idesc_qk128, kk != 0);
-          }
-          tc_commit(&s_full[2 * i]);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          umma_ss(tmem + kColS + i * 128, make_sdesc_sw128(sq_addr + i * kTileBytes + off, 0, 1024),
+                  make_sdesc_sw128(k_addr + off, 0, 1024), idesc_qk, kk != 0);
         }
+        tc_commit(&s_full[i]);
       };
       // O_i += P_i V : contraction over kv, 8 steps of 16 rows (2048 B); V is [kv][d] = MN-major B with two
       // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO)
@@ -211,7 +194,6 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8,
                     make_sdesc_sw128(v_addr + kk * 2048, kHalfBytes, 1024), idesc_pv, accumulate || kk != 0);
           }
-          if (half == 0) tc_commit(&o_half[i]);
         }
       };
       mbar_wait(q_full, 0);
@@ -251,230 +233,99 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const float sl2 = p.sl2;
     float m_run = -INFINITY, l_run = 0.f;
 
-    // scales O (TMEM) and the running sum by 2^((m_run - m_new) * sl2) per row and adopts the new reference maximum
-    auto rescale = [&](float m_new) {
-      const float alpha = ex2((m_run - m_new) * sl2);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t o[32];
-        tmem_ld32(t_o + c * 32, o);
-        tmem_ld_wait();
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[grp], j & 1);
+      tc_fence_after();
+      const int n_valid = min(kTile, p.Skv - j * kTile);
+      // the whole score row in registers: four 32-column TMEM loads in flight, one wait
+      uint32_t v[128];
+      tmem_ld32p(t_s, v);
+      tmem_ld32p(t_s + 32, v + 32);
+      tmem_ld32p(t_s + 64, v + 64);
+      tmem_ld32p(t_s + 96, v + 96);
+      tmem_ld_wait();
+      if (n_valid < kTile) {  // KV tail (last tile only): masked columns behave as -inf
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
-        tmem_st32(t_o + c * 32, o);
+        for (int jj = 0; jj < 128; ++jj)
+          if (jj >= n_valid) v[jj] = 0xff800000u;
       }
-      tmem_st_wait();
-      l_run *= alpha;
-      m_run = m_new;
-      return alpha;
-    };
-    // maximum of 64 raw scores, four independent FMNMX3 chains
-    auto max64 = [&](const uint32_t* v) {
+      // row maximum of the raw scores, four independent chains
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int jj = 0; jj < 64; jj += 8) {
+      for (int jj = 0; jj < 128; jj += 8) {   // FMNMX3: one instruction per two scores
         mx0 = max3f(mx0, __uint_as_float(v[jj + 0]), __uint_as_float(v[jj + 1]));
         mx1 = max3f(mx1, __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
         mx2 = max3f(mx2, __uint_as_float(v[jj + 4]), __uint_as_float(v[jj + 5]));
         mx3 = max3f(mx3, __uint_as_float(v[jj + 6]), __uint_as_float(v[jj + 7]));
       }
-      return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-    };
-    // P = exp2(s * sl2 - m * sl2) for 64 scores, packed bf16 pairs into v[0..32) (in place); returns the row-sum part
-    auto exp64 = [&](uint32_t* v) {
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (j == 0) {
+        m_run = mx;
+      } else {
+        const bool need = (mx - m_run) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // O_i must be quiescent: PV_i(j-1) complete, PV_i(j) not issued before our p_full arrive
+          mbar_wait(&o_bar[grp], (j - 1) & 1);
+          tc_fence_after();
+          const float m_new = need ? mx : m_run;
+          const float alpha = ex2((m_run - m_new) * sl2);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
+            tmem_st32(t_o + c * 32, o);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_run = m_new;
+        }
+      }
+      // pass 2: P = exp2((s - m) * scale * log2 e), packed bf16 pairs into the first 64 columns of S_i. Scale-and-shift
+      // and the row sum run as packed FFMA2 / FADD2 (one issue slot per two scores).
       const uint64_t sl2_2 = pack2f(sl2, sl2);
       const float neg_m = -m_run * sl2;
       const uint64_t neg_m2 = pack2f(neg_m, neg_m);
       uint64_t sum_a = pack2f(0.f, 0.f), sum_b = sum_a;
 #pragma unroll
-      for (int jj = 0; jj < 64; jj += 4) {
-        const uint64_t xa = fma2(pack2u(v[jj + 0], v[jj + 1]), sl2_2, neg_m2);
-        const uint64_t xb = fma2(pack2u(v[jj + 2], v[jj + 3]), sl2_2, neg_m2);
-        float p0, p1, p2, p3;
-        if (poly_pair(kPoly, (jj >> 1) & 7)) {
-          ex2_poly2(xa, p0, p1);
-        } else {
-          unpack2f(xa, p0, p1);
-          p0 = ex2(p0);
-          p1 = ex2(p1);
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int jj = 64 * half; jj < 64 * half + 64; jj += 4) {
+          const uint64_t xa = fma2(pack2u(v[jj + 0], v[jj + 1]), sl2_2, neg_m2);
+          const uint64_t xb = fma2(pack2u(v[jj + 2], v[jj + 3]), sl2_2, neg_m2);
+          float p0, p1, p2, p3;
+          if (poly_pair(kPoly, (jj >> 1) & 7)) {
+            ex2_poly2(xa, p0, p1);
+          } else {
+            unpack2f(xa, p0, p1);
+            p0 = ex2(p0);
+            p1 = ex2(p1);
+          }
+          if (poly_pair(kPoly, ((jj >> 1) + 1) & 7)) {
+            ex2_poly2(xb, p2, p3);
+          } else {
+            unpack2f(xb, p2, p3);
+            p2 = ex2(p2);
+            p3 = ex2(p3);
+          }
+          sum_a = add2(sum_a, pack2f(p0, p1));
+          sum_b = add2(sum_b, pack2f(p2, p3));
+          v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
+          v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
         }
-        if (poly_pair(kPoly, ((jj >> 1) + 1) & 7)) {
-          ex2_poly2(xb, p2, p3);
-        } else {
-          unpack2f(xb, p2, p3);
-          p2 = ex2(p2);
-          p3 = ex2(p3);
-        }
-        sum_a = add2(sum_a, pack2f(p0, p1));
-        sum_b = add2(sum_b, pack2f(p2, p3));
-        v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
-        v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
+        // publish this half of P (32 TMEM columns = 64 kv positions) so its PV MMAs can start
+        tmem_st32p(t_s + 32 * half, v + 32 * half);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_half[2 * grp + half]);
       }
-      float s0, s1, s2, s3;
-      unpack2f(sum_a, s0, s1);
-      unpack2f(sum_b, s2, s3);
-      return (s0 + s1) + (s2 + s3);
-    };
-    // publishes one half of P (32 TMEM columns = 64 kv positions) so that its four P V MMAs can start
-    auto publish = [&](int half, const uint32_t* v) {
-      tmem_st32p(t_s + 32 * half, v);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_half[2 * grp + half]);
-    };
-
-    if constexpr (kPipe) {
-      for (int j = 0; j < n_tiles; ++j) {
-        const int n_valid = min(kTile, p.Skv - j * kTile);
-        uint32_t a[64], b[64];
-        // ---- half 0 into registers; half 1's TMEM loads stay in flight while half 0 is exponentiated
-        mbar_wait(&s_full[2 * grp], j & 1);
-        tc_fence_after();
-        tmem_ld32p(t_s, a);
-        tmem_ld32p(t_s + 32, a + 32);
-        tmem_ld_wait();
-        mbar_wait(&s_full[2 * grp + 1], j & 1);
-        tc_fence_after();
-        tmem_ld32p(t_s + 64, b);
-        tmem_ld32p(t_s + 96, b + 32);
-        if (n_valid < 64) {   // KV tail (last tile only): masked columns behave as -inf
-  #pragma unroll
-          for (int jj = 0; jj < 64; ++jj)
-            if (jj >= n_valid) a[jj] = 0xff800000u;
-        }
-        const float mx_a = max64(a);
-        if (j == 0) {
-          m_run = mx_a;
-        } else {
-          const bool need = (mx_a - m_run) * sl2 > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            // O_i must be quiescent: PV_i(j-1) complete, PV_i(j) not issued before our p_half arrive
-            mbar_wait(&o_bar[grp], (j - 1) & 1);
-            tc_fence_after();
-            rescale(need ? mx_a : m_run);
-          }
-        }
-        const float sum_a = exp64(a);
-        publish(0, a);
-        // ---- half 1
-        tmem_ld_wait();
-        if (n_valid < kTile) {
-  #pragma unroll
-          for (int jj = 0; jj < 64; ++jj)
-            if (64 + jj >= n_valid) b[jj] = 0xff800000u;
-        }
-        const float mx_b = max64(b);
-        float sum_a_scaled = sum_a;
-        {
-          const bool need = (mx_b - m_run) * sl2 > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            // half 0 of this tile is already accumulating into O with the old reference: wait for exactly those MMAs
-            // (PV_i half 1 cannot start before our second p_half arrive), then rescale O, the running sum and half 0's sum
-            mbar_wait(&o_half[grp], j & 1);
-            tc_fence_after();
-            sum_a_scaled *= rescale(need ? mx_b : m_run);
-          }
-        }
-        const float sum_b = exp64(b);
-        publish(1, b);
-        l_run += sum_a_scaled + sum_b;
-      }
-    } else {
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&s_full[2 * grp], j & 1);
-        tc_fence_after();
-        const int n_valid = min(kTile, p.Skv - j * kTile);
-        // the whole score row in registers: four 32-column TMEM loads in flight, one wait
-        uint32_t v[128];
-        tmem_ld32p(t_s, v);
-        tmem_ld32p(t_s + 32, v + 32);
-        tmem_ld32p(t_s + 64, v + 64);
-        tmem_ld32p(t_s + 96, v + 96);
-        tmem_ld_wait();
-        if (n_valid < kTile) {  // KV tail (last tile only): masked columns behave as -inf
-  #pragma unroll
-          for (int jj = 0; jj < 128; ++jj)
-            if (jj >= n_valid) v[jj] = 0xff800000u;
-        }
-        // row maximum of the raw scores, four independent chains
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-  #pragma unroll
-        for (int jj = 0; jj < 128; jj += 8) {   // FMNMX3: one instruction per two scores
-          mx0 = max3f(mx0, __uint_as_float(v[jj + 0]), __uint_as_float(v[jj + 1]));
-          mx1 = max3f(mx1, __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
-          mx2 = max3f(mx2, __uint_as_float(v[jj + 4]), __uint_as_float(v[jj + 5]));
-          mx3 = max3f(mx3, __uint_as_float(v[jj + 6]), __uint_as_float(v[jj + 7]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (j == 0) {
-          m_run = mx;
-        } else {
-          const bool need = (mx - m_run) * sl2 > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            // O_i must be quiescent: PV_i(j-1) complete, PV_i(j) not issued before our p_full arrive
-            mbar_wait(&o_bar[grp], (j - 1) & 1);
-            tc_fence_after();
-            const float m_new = need ? mx : m_run;
-            const float alpha = ex2((m_run - m_new) * sl2);
-  #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t o[32];
-              tmem_ld32(t_o + c * 32, o);
-              tmem_ld_wait();
-  #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) o[jj] = __float_as_uint(__uint_as_float(o[jj]) * alpha);
-              tmem_st32(t_o + c * 32, o);
-            }
-            tmem_st_wait();
-            l_run *= alpha;
-            m_run = m_new;
-          }
-        }
-        // pass 2: P = exp2((s - m) * scale * log2 e), packed bf16 pairs into the first 64 columns of S_i. Scale-and-shift
-        // and the row sum run as packed FFMA2 / FADD2 (one issue slot per two scores).
-        const uint64_t sl2_2 = pack2f(sl2, sl2);
-        const float neg_m = -m_run * sl2;
-        const uint64_t neg_m2 = pack2f(neg_m, neg_m);
-        uint64_t sum_a = pack2f(0.f, 0.f), sum_b = sum_a;
-  #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-  #pragma unroll
-          for (int jj = 64 * half; jj < 64 * half + 64; jj += 4) {
-            const uint64_t xa = fma2(pack2u(v[jj + 0], v[jj + 1]), sl2_2, neg_m2);
-            const uint64_t xb = fma2(pack2u(v[jj + 2], v[jj + 3]), sl2_2, neg_m2);
-            float p0, p1, p2, p3;
-            if (poly_pair(kPoly, (jj >> 1) & 7)) {
-              ex2_poly2(xa, p0, p1);
-            } else {
-              unpack2f(xa, p0, p1);
-              p0 = ex2(p0);
-              p1 = ex2(p1);
-            }
-            if (poly_pair(kPoly, ((jj >> 1) + 1) & 7)) {
-              ex2_poly2(xb, p2, p3);
-            } else {
-              unpack2f(xb, p2, p3);
-              p2 = ex2(p2);
-              p3 = ex2(p3);
-            }
-            sum_a = add2(sum_a, pack2f(p0, p1));
-            sum_b = add2(sum_b, pack2f(p2, p3));
-            v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
-            v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
-          }
-          // publish this half of P (32 TMEM columns = 64 kv positions) so its PV MMAs can start
-          tmem_st32p(t_s + 32 * half, v + 32 * half);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_half[2 * grp + half]);
-        }
-        float sum0, sum1, sum2, sum3;
-        unpack2f(sum_a, sum0, sum1);
-        unpack2f(sum_b, sum2, sum3);
-        l_run += (sum0 + sum1) + (sum2 + sum3);
-      }
+      float sum0, sum1, sum2, sum3;
+      unpack2f(sum_a, sum0, sum1);
+      unpack2f(sum_b, sum2, sum3);
+      l_run += (sum0 + sum1) + (sum2 + sum3);
     }
     // epilogue: O_i / l -> bf16 -> global
     mbar_wait(&o_bar[grp], (n_tiles - 1) & 1);
@@ -512,25 +363,20 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
   if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
-  // tuning knobs: attn_poly (0, 2, 3 or 4 of every 8 exponential pairs on the FMA pipe instead of MUFU) and attn_pipe
-  // (1: two software-pipelined 64-column halves per score tile; 0: whole row in registers before the first exponential)
+  // tuning knob attn_poly / RGE_ATTN_POLY: 0 (default, fastest measured), 2, 3 or 4 of every 8 exponential pairs on the
+  // FMA pipe instead of MUFU
   int poly = tuning().attn_poly;
   if (poly < 0) poly = kDefaultPoly;
   if (poly != 2 && poly != 3 && poly != 4) poly = 0;
-  int pipe = tuning().attn_pipe;
-  if (pipe < 0) pipe = kDefaultPipe;
   typedef void (*Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
-  static const Kernel table[2][4] = {
-      {attention_kernel<0, false>, attention_kernel<2, false>, attention_kernel<3, false>, attention_kernel<4, false>},
-      {attention_kernel<0, true>, attention_kernel<2, true>, attention_kernel<3, true>, attention_kernel<4, true>}};
+  static const Kernel table[4] = {attention_kernel<0>, attention_kernel<2>, attention_kernel<3>, attention_kernel<4>};
   const int dev = current_device();
   static bool attr_set[kMaxDevices] = {};   // per device: a process may drive several GPUs
   if (!attr_set[dev]) {
-    for (int i = 0; i < 2; ++i)
-      for (int k = 0; k < 4; ++k) {
-        cudaError_t e = cudaFuncSetAttribute(table[i][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return e;
-      }
+    for (int k = 0; k < 4; ++k) {
+      cudaError_t e = cudaFuncSetAttribute(table[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) return e;
+    }
     attr_set[dev] = true;
   }
   CUtensorMap mq, mk, mv;
@@ -544,7 +390,7 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.Skv = a.Skv;
   p.sl2 = a.scale * 1.4426950408889634f;
   dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
-  table[pipe ? 1 : 0][poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  table[poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
 

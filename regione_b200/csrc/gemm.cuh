@@ -46,10 +46,6 @@ cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // Up to 6 independent GEMMs (1-CTA tiles) as one persistent launch; members with M <= 0 are skipped.
 cudaError_t launch_gemm_group(const GemmArgs* args, int n, int num_sms, cudaStream_t stream);
 
-// Grouped CTA-pair kernel (gemm3.cu): up to 6 members with N % 256 == 0 as one persistent launch over whole 256 x 256
-// tiles. Returns cudaErrorNotSupported if a member is outside the envelope (nothing launched).
-cudaError_t launch_gemm_group2(const GemmArgs* args, int n, int num_sms, cudaStream_t stream);
-bool group2_eligible(const GemmArgs& a);
 bool gemm_args_valid(const GemmArgs& a);   // strides, alignment and epilogue operands acceptable to every kernel
 size_t streamk_workspace_bytes(int num_sms);
 size_t streamk_flag_bytes(int num_sms);

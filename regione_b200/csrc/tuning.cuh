@@ -18,13 +18,10 @@ inline int current_device() {
 
 struct Tuning {
   int attn_poly;     // RGE_ATTN_POLY:   exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
-  int attn_pipe;     // RGE_ATTN_PIPE:   1 = score tile in two software-pipelined halves, 0 = whole row first, -1 = default
   int attn_split;    // RGE_ATTN_SPLIT:  KV splits of the attention grid, 0 = choose per launch
   int gemm_bn;       // RGE_GEMM_BN:     forced tile width of the 1-CTA GEMM, 0 = choose per launch
   int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never
   int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
-  int gemm3;         // RGE_GEMM3:       1 = grouped launches go to the grouped CTA-pair kernel (gemm3.cu) when every
-                     //                  member has N % 256 == 0, else to the grouped 1-CTA kernel
   int trim_last;     // RGE_TRIM_LAST:   1 = the last block computes only the rows whose output is kept (default)
   int nvtx;          // RGE_NVTX:        1 = NVTX ranges per step / block / stage (profilers only)
 };
@@ -38,13 +35,11 @@ inline Tuning& tuning() {
   static Tuning t = [] {
     Tuning x;
     x.attn_poly = env_int("RGE_ATTN_POLY", -1);
-    x.attn_pipe = env_int("RGE_ATTN_PIPE", -1);
     x.attn_split = env_int("RGE_ATTN_SPLIT", 0);
     x.gemm_bn = env_int("RGE_GEMM_BN", 0);
     x.min_m_2cta = env_int("RGE_2CTA_MIN_M", 2048);
     const char* r = getenv("RGE_RASTER");
     x.raster = !r ? -1 : (r[0] == 'n' ? 1 : (r[0] == 'm' ? 0 : -1));
-    x.gemm3 = env_int("RGE_GEMM3", 0);
     x.trim_last = env_int("RGE_TRIM_LAST", 1);
     x.nvtx = env_int("RGE_NVTX", 0);
     return x;
@@ -56,12 +51,10 @@ inline Tuning& tuning() {
 inline bool set_tuning(const char* name, int value) {
   Tuning& t = tuning();
   if (!strcmp(name, "attn_poly")) t.attn_poly = value;
-  else if (!strcmp(name, "attn_pipe")) t.attn_pipe = value;
   else if (!strcmp(name, "attn_split")) t.attn_split = value;
   else if (!strcmp(name, "gemm_bn")) t.gemm_bn = value;
   else if (!strcmp(name, "2cta_min_m")) t.min_m_2cta = value;
   else if (!strcmp(name, "raster")) t.raster = value;
-  else if (!strcmp(name, "gemm3")) t.gemm3 = value;
   else if (!strcmp(name, "trim_last")) t.trim_last = value;
   else if (!strcmp(name, "nvtx")) t.nvtx = value;
   else return false;

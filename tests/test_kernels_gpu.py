@@ -213,14 +213,11 @@ def test_attention_matches_exact_softmax(Sq, Skv, H):
     assert rel_l2(o, ref) <= 6e-3                                  # bf16 P and bf16 output
 
 
-@pytest.mark.parametrize("pipe", [0, 1])
 @pytest.mark.parametrize("poly", [0, 2, 3, 4])
-def test_attention_exponential_offload_variants(poly, pipe):
+def test_attention_exponential_offload_variants(poly):
     """`attn_poly` of every 8 exponential pairs run as a Cody-Waite / degree-3 polynomial on the FMA pipe instead of
     MUFU.EX2 (relative error 7.5e-5, below the bf16 rounding of P): every variant stays within the same tolerance of
-    the exact softmax, including rows with large late keys (lazy rescale) and a ragged KV tail (masked columns).
-    `attn_pipe` = 1 processes each score tile as two software-pipelined 64-column halves (reference maximum decided per
-    half; a late large key in half 1 takes the wait-for-half-0's-MMAs rescale path)."""
+    the exact softmax, including rows with large late keys (lazy rescale) and a ragged KV tail (masked columns)."""
     from regione_b200 import ops
     g = _gen(21)
     Sq, Skv, H = 777, 2100, 3
@@ -230,16 +227,14 @@ def test_attention_exponential_offload_variants(poly, pipe):
     k[Skv // 2:] *= 3.0
     q[:64] *= 6.0                                                   # peaked rows: scores far below the row maximum
     hd = lambda t: t.view(1, -1, H, 128).transpose(1, 2)          # noqa: E731
-    k[Skv // 2 + 70: Skv // 2 + 90] *= 4.0                          # a jump INSIDE the second half of a tile
+    k[Skv // 2 + 70: Skv // 2 + 90] *= 4.0                          # a second jump inside a tile
     ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
     ops.set_option("attn_poly", poly)
-    ops.set_option("attn_pipe", pipe)
     try:
         o = ops.attention(q, k, v, H)
         torch.cuda.synchronize()
     finally:
         ops.set_option("attn_poly", -1)
-        ops.set_option("attn_pipe", -1)
     assert torch.isfinite(o.float()).all()
     assert rel_l2(o, ref) <= 6e-3
 
@@ -453,59 +448,3 @@ def test_gemm_group_equals_single_launches():
     assert rel_l2(got[2][sel.long()], F.linear(x_img, wv, bv)) <= BF16_TOL
     assert rel_l2(got[3][:, D:], F.gelu(F.linear(x_img, wm, bm), approximate="tanh")) <= BF16_TOL
     assert rel_l2(got[4], res0 + gate[None] * F.linear(hid, wdown, bdown)) <= BF16_TOL
-
-
-def test_gemm3_grouped_cta_pair_kernel_bit_identical_with_whole_tiles():
-    """gemm3.cu (`gemm3 = 1`): up to 6 GEMMs as one persistent CTA-pair launch over whole 256 x 256 tiles. Same
-    MMA shape and K order as the CTA-pair kernel, so every epilogue must be BIT-IDENTICAL to the members launched one by
-    one on it (2cta_min_m = 1 forces that kernel for the small members)."""
-    from regione_b200 import _lib, ops
-    g = _gen(61)
-    D, Dm, S, T, M = 512, 1024, 2600, 200, 1064
-
-    def lin(n, k):
-        return ((torch.randn(n, k, device="cuda", generator=g) * 0.05).bfloat16(),
-                torch.randn(n, device="cuda", generator=g).bfloat16())
-
-    x_img = torch.randn(M, D, device="cuda", generator=g).bfloat16()
-    x_txt = torch.randn(T, D, device="cuda", generator=g).bfloat16()
-    sel = (torch.randperm(S - T, device="cuda", generator=g)[:M].sort().values + T).int()
-    nw = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
-    cs = torch.randn(S, 64, 2, device="cuda", generator=g)
-    (wq, bq), (wk, bk), (wv, bv), (wm, bm) = lin(D, D), lin(D, D), lin(D, D), lin(Dm, D)
-    (wtq, btq), (wdown, bdown) = lin(D, D), lin(D, Dm)
-    gate = torch.randn(D, device="cuda", generator=g).bfloat16()
-    hid = torch.randn(M, Dm, device="cuda", generator=g).bfloat16()
-    res0 = torch.randn(M, D, device="cuda", generator=g).bfloat16()
-
-    def members(q, kc, vc, big, res):
-        return [
-            (x_img, wq, bq, dict(epilogue=_lib.EPI_NORM_ROPE, out=q, row_off=T, norm_w=nw, rope_cs=cs, rope_map=sel)),
-            (x_img, wk, bk, dict(epilogue=_lib.EPI_NORM_ROPE, out=kc, row_map=sel, norm_w=nw, rope_cs=cs, rope_map=sel)),
-            (x_img, wv, bv, dict(out=vc, row_map=sel)),
-            (x_txt, wtq, btq, dict(epilogue=_lib.EPI_NORM_ROPE, out=q, norm_w=nw, rope_cs=cs)),
-            (x_img, wm, bm, dict(epilogue=_lib.EPI_GELU, out=big, col_off=D)),
-            (hid, wdown, bdown, dict(epilogue=_lib.EPI_GATE_RES, out=res, gate=gate, res=res)),
-        ]
-
-    def buffers():
-        return (torch.zeros(T + M, D, device="cuda", dtype=torch.bfloat16),
-                torch.zeros(S, D, device="cuda", dtype=torch.bfloat16),
-                torch.zeros(S, D, device="cuda", dtype=torch.bfloat16),
-                torch.zeros(M, D + Dm, device="cuda", dtype=torch.bfloat16), res0.clone())
-
-    try:
-        ops.set_option("2cta_min_m", 1)
-        ref = buffers()
-        for a, w, b, kw in members(*ref):
-            ops.gemm(a, w, b, **kw)
-        ops.set_option("gemm3", 1)
-        got = buffers()
-        ops.gemm_group(members(*got))
-        torch.cuda.synchronize()
-        for r, o in zip(ref, got):
-            assert torch.equal(r, o)
-    finally:
-        ops.set_option("gemm3", 0)
-        ops.set_option("2cta_min_m", 2048)
-    assert rel_l2(got[2][sel.long()], F.linear(x_img, wv, bv)) <= BF16_TOL

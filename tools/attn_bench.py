@@ -41,13 +41,10 @@ def main():
         o = torch.empty_like(q)
         fl = 4.0 * Sq * Skv * 128 * H
         res = {}
-        for pipe in (0, 1):
-            for poly in (0, 2, 4):
-                ops.set_option("attn_poly", poly)
-                ops.set_option("attn_pipe", pipe)
-                res[f"ours pipe={pipe} poly={poly}"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
+        for poly in (0, 2, 4):
+            ops.set_option("attn_poly", poly)
+            res[f"ours poly={poly}"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         ops.set_option("attn_poly", -1)
-        ops.set_option("attn_pipe", -1)
         res["ours default"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         try:
             from flash_attn import flash_attn_func

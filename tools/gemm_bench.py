@@ -58,12 +58,6 @@ def main():
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=pos)
             fns["ours_norm_rope(pair-major table)"] = lambda: ops.gemm(
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_map=pos, rope_ld=S)
-        if N % 256 == 0:                     # gemm3.cu: the grouped CTA-pair kernel with a single member
-            def g3():
-                ops.set_option("gemm3", 1)
-                ops.gemm_group([(a, w, b, dict(out=out))])
-                ops.set_option("gemm3", 0)
-            fns["gemm3 (1 member)"] = g3
         if M < 2048 and N % 256 == 0:        # the CTA-pair kernel below its default row threshold
             def pair():
                 ops.set_option("2cta_min_m", 1)
@@ -80,7 +74,7 @@ def main():
             time.sleep(0.2)
         print(f"M={M} N={N} K={K}: " + "  |  ".join(
             f"{k} {v[0]:.0f}/{v[1]:.0f}" for k, v in res.items()) + "   (burst/sustained TF/s)", flush=True)
-    # ---- the q / k / v (+ text q / k / v) projections of one double block as ONE launch (gemm3) vs six launches
+    # ---- the q / k / v (+ text q / k / v) projections of one double block as ONE grouped launch vs six launches
     D, S = 3072, 8704
     nw = torch.ones(128, device="cuda").bfloat16()
     cs_pm = torch.randn(64, S, 2, device="cuda")
@@ -105,15 +99,8 @@ def main():
             for a_, w_, b_, kw in members:
                 ops.gemm(a_, w_, b_, **kw)
 
-        def grouped(mode):
-            def run():
-                ops.set_option("gemm3", mode)
-                ops.gemm_group(members)
-                ops.set_option("gemm3", 0)
-            return run
         r = {}
-        for name, fn in (("six launches (one stream)", six), ("1-CTA grouped kernel", lambda: ops.gemm_group(members)),
-                         ("gemm3 grouped CTA-pair kernel", grouped(1))):
+        for name, fn in (("six launches (one stream)", six), ("grouped kernel", lambda: ops.gemm_group(members))):
             for _ in range(3):
                 fn()
             r[name] = timeit(fn, secs)
