@@ -103,8 +103,8 @@ def cpu_reference_sample(n_edited: int, region_steps: int, repeats: int = 1):
     measured, description)."""
     from oracle.flux import FluxOracle
     from oracle import region_ops as ro
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -158,7 +158,7 @@ def run_ours(args):
     import torch.distributed as dist
     from regione_b200 import RegionEHelper, _lib
     from regione_b200 import flux_kontext as fk
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -393,8 +393,8 @@ def reference_gpu_images(args, pipe, n_timed: int, n_warm: int) -> dict:
     from oracle.build_ref import load_partially_linear
     from oracle.loop import run_regione
     from oracle.schedule import GAMMA
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     dev = pipe.transformer.x_embedder.weight.device
 
@@ -450,7 +450,7 @@ def reference_gpu_images(args, pipe, n_timed: int, n_warm: int) -> dict:
 
 def run_reference_gpu(args):
     """`--impl reference_gpu`: only the reference-equivalent GPU arm (the default N = 1 run of our arm embeds it)."""
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     pipe = syn.build_pipeline(syn.FLUX_KONTEXT, seed=110, device=torch.device("cuda", 0))
     ref = reference_gpu_images(args, pipe, args.steps, args.warmup)
     print(json.dumps({

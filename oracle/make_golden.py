@@ -278,7 +278,7 @@ def make_cfg():
     velocities: Step1XEdit/inplace.py:401-410 (norm-processed, above and below `timesteps_truncate`; `process_diff_norm`
     is the fork's function, absent here -> the stand-in the product tests use, passed in as `self`) and
     QwenImageEdit/inplace.py:401-405 (norm rescaling)."""
-    from regione_b200.standin_step1x import Step1XEditPipeline
+    from standins.step1x import Step1XEditPipeline
     g = torch.Generator().manual_seed(5)
     pos = torch.randn(1, 512, 64, generator=g).bfloat16()
     neg = (pos.float() + 0.5 * torch.randn(1, 512, 64, generator=g)).bfloat16()

@@ -114,8 +114,12 @@ def _shard(items):
 
 def _synthetic(family: str, args):
     """Stand-in pipeline of the family + a function item_key -> call keywords (seeded synthetic latents / embeds)."""
-    from . import standin, standin_step1x as sx
-    from . import synthetic as syn
+    try:   # test / benchmark scaffolding that lives next to the package, not in it
+        from standins import diffusers_like as standin, step1x as sx
+        from standins import synthetic as syn
+    except ImportError as e:
+        raise SystemExit("regione_b200.cli: --model_path synthetic needs the repository's `standins` package on "
+                         "sys.path (run from the repository root)") from e
 
     tiny = args.model_path.endswith(":tiny")
     dev = torch.device(args.device)

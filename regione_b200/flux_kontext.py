@@ -305,7 +305,7 @@ class RegionEFluxKontextPipelineMixin:
             if image_ids is not None:
                 latent_ids = torch.cat([latent_ids, image_ids], dim=0)
         else:
-            from .standin import latent_image_ids
+            from .schedule import latent_image_ids
             if height is None or width is None:
                 raise ValueError("height and width are required with packed latents")
             gh, gw = height // multiple_of, width // multiple_of

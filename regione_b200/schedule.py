@@ -2,6 +2,8 @@
 (RegionE/FluxKontext/utils.py:38-107, identical in every family) — same names, arguments and error behaviour."""
 from __future__ import annotations
 
+import torch
+
 import inspect
 
 
@@ -39,3 +41,12 @@ def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timeste
         scheduler.set_timesteps(num_inference_steps, device=device, **kwargs)
         timesteps = scheduler.timesteps
     return timesteps, num_inference_steps
+
+
+def latent_image_ids(grid_h: int, grid_w: int, first: float = 0.0, device="cpu", dtype=torch.float32):
+    """diffusers FluxKontextPipeline._prepare_latent_image_ids: rows (first, r, c), row-major."""
+    ids = torch.zeros(grid_h, grid_w, 3)
+    ids[..., 0] = first
+    ids[..., 1] = torch.arange(grid_h)[:, None]
+    ids[..., 2] = torch.arange(grid_w)[None, :]
+    return ids.reshape(grid_h * grid_w, 3).to(device=device, dtype=dtype)

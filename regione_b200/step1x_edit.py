@@ -130,7 +130,7 @@ class RegionEStep1XEditPipelineMixin:
             raise NotImplementedError(LATENT_SPACE_ONLY)
         if height is None or width is None:
             raise ValueError("height and width are required with packed latents")
-        from .standin import latent_image_ids
+        from .schedule import latent_image_ids
         device = self._execution_device
         gh, gw = height // (self.vae_scale_factor * 2), width // (self.vae_scale_factor * 2)
         assert latents.shape[1] == gh * gw and image_latents.shape[1] == gh * gw, "latents do not match H x W"

@@ -79,7 +79,7 @@ class RegionEStep1XEditV1P2PipelineMixin:
             raise NotImplementedError(LATENT_SPACE_ONLY)
         if height is None or width is None:
             raise ValueError("height and width are required with packed latents")
-        from .standin import latent_image_ids
+        from .schedule import latent_image_ids
         device = self._execution_device
         self._joint_attention_kwargs = joint_attention_kwargs or {}
         gh, gw = height // (self.vae_scale_factor * 2), width // (self.vae_scale_factor * 2)

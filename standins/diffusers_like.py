@@ -4,6 +4,9 @@ FlowMatchEulerDiscreteScheduler with the fields the reference reads, and a `Flux
 what `RegionEHelper` dispatches on (RegionE/tool/RegionE.py:12-13). They carry synthetic weights at real or reduced
 shapes for tests and benchmarks. None of this is on the hot path: after `RegionEHelper.enable()` every forward runs
 in the CUDA library; the un-patched (vanilla) forward belongs to diffusers and is deliberately not re-implemented.
+
+TEST / BENCHMARK SCAFFOLDING: lives outside the product package (`regione_b200/` never imports it, except the CLI's
+`--model_path synthetic` mode, lazily).
 """
 from __future__ import annotations
 
@@ -190,13 +193,7 @@ class FlowMatchEulerDiscreteScheduler:
         return (prev,) if not return_dict else SimpleNamespace(prev_sample=prev)
 
 
-def latent_image_ids(grid_h: int, grid_w: int, first: float = 0.0, device="cpu", dtype=torch.float32):
-    """diffusers FluxKontextPipeline._prepare_latent_image_ids: rows (first, r, c), row-major."""
-    ids = torch.zeros(grid_h, grid_w, 3)
-    ids[..., 0] = first
-    ids[..., 1] = torch.arange(grid_h)[:, None]
-    ids[..., 2] = torch.arange(grid_w)[None, :]
-    return ids.reshape(grid_h * grid_w, 3).to(device=device, dtype=dtype)
+from regione_b200.schedule import latent_image_ids  # noqa: E402,F401  (re-exported: part of the product)
 
 
 class FluxKontextPipeline:

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .standin import (FlowMatchEulerDiscreteScheduler, FluxKontextPipeline, FluxTransformer2DModel, _AdaNorm,
+from .diffusers_like import (FlowMatchEulerDiscreteScheduler, FluxKontextPipeline, FluxTransformer2DModel, _AdaNorm,
                       _Config, _DoubleBlock, _SingleBlock)
 
 

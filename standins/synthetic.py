@@ -11,7 +11,7 @@ import math
 
 import torch
 
-from .standin import FlowMatchEulerDiscreteScheduler, FluxKontextPipeline, FluxTransformer2DModel
+from .diffusers_like import FlowMatchEulerDiscreteScheduler, FluxKontextPipeline, FluxTransformer2DModel
 
 FLUX_KONTEXT = dict(dim=3072, heads=24, n_double=19, n_single=38, mlp_ratio=4, in_channels=64, ctx_dim=4096,
                     pooled_dim=768, guidance_embeds=True)

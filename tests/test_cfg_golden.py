@@ -16,7 +16,7 @@ def golden(golden_dir):
 def test_oracle_cfg_functions_match_reference_lines(golden):
     from oracle.qwen import cfg_norm_rescaled
     from oracle.step1x import cfg_norm_processed
-    from regione_b200.standin_step1x import Step1XEditPipeline
+    from standins.step1x import Step1XEditPipeline
     pos, neg = golden["pos"], golden["neg"]
     assert len(golden["step1x"]) == 3 and len(golden["qwen"]) == 2
     for c in golden["step1x"]:
@@ -30,7 +30,7 @@ def test_oracle_cfg_functions_match_reference_lines(golden):
 @pytest.mark.gpu
 def test_cuda_cfg_kernels_match_reference_lines(golden):
     from regione_b200 import ops
-    from regione_b200.standin_step1x import Step1XEditPipeline
+    from standins.step1x import Step1XEditPipeline
     pos, neg = golden["pos"][0].cuda(), golden["neg"][0].cuda()
 
     def close(got, want):

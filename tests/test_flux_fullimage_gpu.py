@@ -25,8 +25,8 @@ def rel_l2(a, b):
 
 def test_whole_image_at_baseline_shapes_and_depth():
     from regione_b200 import RegionEHelper
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     dev = "cuda"
     arch, G, T = syn.FLUX_KONTEXT, 64, 512

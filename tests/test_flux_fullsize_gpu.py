@@ -16,9 +16,9 @@ def rel_l2(a, b):
 
 
 def test_full_and_region_step_at_baseline_shapes():
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     from regione_b200.engine import FluxEngine
-    from regione_b200.standin import latent_image_ids
+    from regione_b200.schedule import latent_image_ids
 
     dev = "cuda"
     arch = dict(syn.FLUX_KONTEXT, n_double=1, n_single=1)

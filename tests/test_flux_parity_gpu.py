@@ -21,8 +21,8 @@ def rel_l2(a, b):
 
 def _run_both(arch, grid, txt_len, rho, params, seed=7, true_cfg_scale=1.0):
     from regione_b200 import RegionEHelper
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     gh, gw = grid
     pipe = syn.build_pipeline(arch, seed=110, device="cpu")
@@ -85,14 +85,14 @@ DEFAULT = dict(warmup_step=6, post_step=2, refresh_step="16", threshold=0.88, ca
 
 
 def test_tiny_flux_default_schedule():
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     worst, final = _check(*_run_both(syn.TINY, (16, 16), 32, 0.25, DEFAULT))
     print(f"tiny: worst velocity rel-L2 {worst:.3e}, final latent rel-L2 {final:.3e}")
 
 
 def test_ragged_grid_and_text_length():
     """Non-square grid, token counts that are not tile multiples, several refresh steps, no morphology."""
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     params = dict(warmup_step=4, post_step=3, refresh_step="10,18", threshold=0.88, cache_threshold=0.01,
                   erosion_dilation=False)
     _check(*_run_both(syn.TINY, (12, 20), 40, 0.4, params, seed=11))
@@ -100,7 +100,7 @@ def test_ragged_grid_and_text_length():
 
 def test_all_tokens_edited():
     """rho = 1: empty unedited set."""
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     ref, ref_tr, out, tr = _run_both(syn.TINY, (16, 16), 32, 1.0, DEFAULT, seed=3)
     assert tr["unedited_ids"].numel() == 0
     _check(ref, ref_tr, out, tr)
@@ -108,7 +108,7 @@ def test_all_tokens_edited():
 
 def test_no_token_edited():
     """rho = 0 without salt noise would still leave stray pixels; with erosion they vanish -> empty edited set."""
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     ref, ref_tr, out, tr = _run_both(syn.TINY, (16, 16), 32, 0.0, DEFAULT, seed=5)
     assert tr["edited_ids"].numel() == ref_tr["edited_ids"].numel()
     _check(ref, ref_tr, out, tr)
@@ -118,14 +118,14 @@ def test_true_cfg_second_forward_shares_the_cache():
     """true_cfg_scale > 1 with a negative prompt (inplace.py:349-364): two forwards per step over ONE K/V cache set,
     like the reference's single per-processor cache. The gate is on latents; the guided velocity amplifies the two
     forwards' independent bf16 rounding by ~the scale, so its own bound scales with it."""
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     ref, ref_tr, out, tr = _run_both(syn.TINY, (16, 16), 32, 0.25, DEFAULT, seed=17, true_cfg_scale=3.0)
     worst, final = _check(ref, ref_tr, out, tr, v_tol=3.0 * TOL)
     print(f"true-CFG 3.0: worst velocity rel-L2 {worst:.3e}, final latent rel-L2 {final:.3e}")
 
 
 def test_wider_model_three_heads():
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     arch = dict(syn.TINY, dim=768, heads=6, n_double=1, n_single=2, ctx_dim=256)
     _check(*_run_both(arch, (16, 16), 64, 0.25, DEFAULT, seed=13))
 
@@ -136,7 +136,7 @@ def test_wider_model_three_heads():
 def test_launch_schedule_variants_give_the_same_image(env, monkeypatch):
     """The engine's launch-schedule knobs (read at rge_create): one grouped launch per stage, attention-tail fill off,
     no side streams. They only reorder independent launches, so every one must pass the same parity gate."""
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _check(*_run_both(syn.TINY, (16, 16), 32, 0.25, DEFAULT))

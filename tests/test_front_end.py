@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from regione_b200 import cli, params, schedule
-from regione_b200.standin import FlowMatchEulerDiscreteScheduler
+from standins.diffusers_like import FlowMatchEulerDiscreteScheduler
 
 
 @pytest.fixture(scope="module")

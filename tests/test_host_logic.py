@@ -9,7 +9,7 @@ import torch
 
 from regione_b200 import RegionEHelper, _lib, helper, params
 from regione_b200 import flux_kontext as fk
-from regione_b200 import standin
+from standins import standin
 from regione_b200.manager import RegionManager, plan_steps
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -142,11 +142,15 @@ def test_product_never_imports_the_oracle():
     import re
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "regione_b200")
     pat = re.compile(r"^\s*(from|import)\s+oracle\b|\boracle\.", re.M)
+    scaffold = re.compile(r"^\s*(from|import)\s+standins\b", re.M)
     checked = 0
     for dirpath, _, files in os.walk(root):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), f"{f} refers to the oracle package"
+                # the duck-typed stand-in pipelines / synthetic inputs are scaffolding too: only the CLI's
+                # `--model_path synthetic` mode may reach for them (lazily, inside the function that needs them)
+                assert f == "cli.py" or not scaffold.search(text), f"{f} imports the test scaffolding"
                 checked += 1
     assert checked > 20

@@ -3,7 +3,8 @@ rotary table's contract, and the not-yet-built families failing loudly."""
 import pytest
 import torch
 
-from regione_b200 import RegionEHelper, params, standin
+from regione_b200 import RegionEHelper, params
+from standins import standin
 from regione_b200 import qwen_image_edit as qw
 
 
@@ -52,7 +53,7 @@ def test_qwen_rope_table_contract():
 
 
 def test_step1x_enable_disable_both_versions():
-    from regione_b200 import standin_step1x as sx
+    from standins import step1x as sx
     from regione_b200 import step1x_edit as s1
     tr = sx.Step1XEditTransformer2DModel(dim=256, heads=2, n_double=1, n_single=1, ctx_dim=64, vec_dim=32)
     pipe = sx.Step1XEditPipeline(tr)

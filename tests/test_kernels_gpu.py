@@ -384,7 +384,7 @@ def test_pack_unpack_latents_bit_exact(B, C, H, W):
     back = ops.unpack_latents(got, H * 8, W * 8, 8)
     ref_back = ref.view(B, H // 2, W // 2, C, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, C, H, W)
     assert torch.equal(back, ref_back) and torch.equal(back, x)
-    from regione_b200.standin import FluxKontextPipeline
+    from standins.diffusers_like import FluxKontextPipeline
     assert torch.equal(FluxKontextPipeline._unpack_latents(FluxKontextPipeline._pack_latents(x), H * 8, W * 8, 8), x)
 
 

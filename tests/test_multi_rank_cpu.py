@@ -15,7 +15,7 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         from regione_b200 import flux_kontext as fk
         from regione_b200 import params
         from regione_b200.manager import RegionManager, plan_steps
-        from regione_b200.standin import FlowMatchEulerDiscreteScheduler
+        from standins.diffusers_like import FlowMatchEulerDiscreteScheduler
         import numpy as np
 
         L = 4096

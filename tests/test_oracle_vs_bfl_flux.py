@@ -197,7 +197,7 @@ def test_sigma_schedule_matches_bfl_flux_sampling():
     import numpy as np
     from oracle.schedule import calculate_shift, flow_match_sigmas
     from regione_b200 import schedule
-    from regione_b200.standin import FlowMatchEulerDiscreteScheduler
+    from standins.diffusers_like import FlowMatchEulerDiscreteScheduler
     for n_tokens in (4096, 4050, 2304, 1024):
         ref = torch.tensor(sampling.get_schedule(28, n_tokens), dtype=torch.float32)          # 29 values, last 0
         sig, ts = flow_match_sigmas(28, n_tokens)

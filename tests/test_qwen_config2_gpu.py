@@ -22,8 +22,9 @@ def rel_l2(a, b):
 
 
 def _run(arch, grid, txt_len, rho, cfg_scale, dev_oracle, velocity_scale, seed=110, floor=False):
-    from regione_b200 import RegionEHelper, params, standin
-    from regione_b200 import synthetic as syn
+    from regione_b200 import RegionEHelper, params
+    from standins import standin
+    from standins import synthetic as syn
 
     table = params.resample_gamma(params.GAMMA["QwenImageEditPipeline"], STEPS)
     p = dict(warmup_step=6, post_step=2, refresh_step="16", threshold=0.80, cache_threshold=0.02, erosion_dilation=True)

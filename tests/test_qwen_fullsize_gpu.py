@@ -19,8 +19,9 @@ def rel_l2(a, b):
 
 
 def test_qwen_full_and_region_step_at_config2_shapes():
-    from regione_b200 import ops, standin
-    from regione_b200 import synthetic as syn
+    from regione_b200 import ops
+    from standins import standin
+    from standins import synthetic as syn
     from regione_b200.engine_qwen import QwenEngine
 
     dev = "cuda"

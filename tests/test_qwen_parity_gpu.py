@@ -15,8 +15,9 @@ def rel_l2(a, b):
 
 
 def _run(grid, txt_len, rho, params, cfg_scale, seed=7, n_blocks=3):
-    from regione_b200 import RegionEHelper, standin
-    from regione_b200 import synthetic as syn
+    from regione_b200 import RegionEHelper
+    from standins import standin
+    from standins import synthetic as syn
 
     gh, gw = grid
     arch = dict(dim=256, heads=2, n_blocks=n_blocks, mlp_ratio=4, in_channels=64, ctx_dim=128)

@@ -20,10 +20,10 @@ def rel_l2(a, b):
 
 def test_step1x_full_and_region_step_at_demo0_shapes():
     from regione_b200 import RegionEHelper
-    from regione_b200 import standin_step1x as sx
+    from standins import step1x as sx
     from regione_b200 import step1x_edit as s1
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     dev = "cuda"
     gh, gw, T = 50, 81, 640

@@ -16,9 +16,9 @@ def rel_l2(a, b):
 
 def _run(grid, txt_len, rho, params, cfg_scale, seed=7):
     from regione_b200 import RegionEHelper
-    from regione_b200 import standin_step1x as sx
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import step1x as sx
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     gh, gw = grid
     arch = dict(dim=256, heads=2, n_double=2, n_single=2, mlp_ratio=4, in_channels=64, ctx_dim=128, vec_dim=64)
@@ -80,7 +80,7 @@ def test_step1x_without_cfg():
 
 def test_step1x_cfg_kernels_bit_exact():
     from regione_b200 import ops
-    from regione_b200.standin_step1x import Step1XEditPipeline
+    from standins.step1x import Step1XEditPipeline
     g = torch.Generator(device="cuda").manual_seed(3)
     pos = torch.randn(1, 4096, 64, device="cuda", generator=g).bfloat16()
     neg = torch.randn(1, 4096, 64, device="cuda", generator=g).bfloat16()

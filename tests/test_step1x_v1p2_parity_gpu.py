@@ -34,9 +34,9 @@ def _to(e, dev):
 
 def test_step1x_v1p2_two_text_lengths():
     from regione_b200 import RegionEHelper, params
-    from regione_b200 import standin_step1x as sx
-    from regione_b200 import synthetic as syn
-    from regione_b200.standin import latent_image_ids
+    from standins import step1x as sx
+    from standins import synthetic as syn
+    from regione_b200.schedule import latent_image_ids
 
     gh, gw, Tc, Tu = 16, 16, 40, 24          # cond prompt longer than the uncond prompt
     arch = dict(dim=256, heads=2, n_double=2, n_single=2, mlp_ratio=4, in_channels=64, ctx_dim=128, vec_dim=64,

@@ -23,9 +23,9 @@ def _both(run):
 
 
 def test_flux_last_single_block_trimmed_bit_identical():
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     from regione_b200.engine import FluxEngine
-    from regione_b200.standin import latent_image_ids
+    from regione_b200.schedule import latent_image_ids
     dev = "cuda"
     arch = dict(dim=512, heads=4, n_double=1, n_single=2, mlp_ratio=4, in_channels=64, ctx_dim=128, pooled_dim=64,
                 guidance_embeds=True)
@@ -53,8 +53,8 @@ def test_flux_last_single_block_trimmed_bit_identical():
 
 
 def test_qwen_last_dual_block_trimmed_bit_identical():
-    from regione_b200 import standin
-    from regione_b200 import synthetic as syn
+    from standins import standin
+    from standins import synthetic as syn
     from regione_b200.engine_qwen import QwenEngine
     dev = "cuda"
     arch = dict(dim=512, heads=4, n_blocks=2, mlp_ratio=4, in_channels=64, ctx_dim=128)

@@ -24,9 +24,9 @@ def main():
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the LAST step of each kind (ncu --profile-from-start off)")
     args = ap.parse_args()
-    from regione_b200 import synthetic as syn
+    from standins import synthetic as syn
     from regione_b200.engine import FluxEngine
-    from regione_b200.standin import latent_image_ids
+    from regione_b200.schedule import latent_image_ids
 
     dev = "cuda"
     arch = dict(syn.FLUX_KONTEXT, n_double=args.blocks[0], n_single=args.blocks[1])

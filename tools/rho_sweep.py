@@ -5,7 +5,7 @@ import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from regione_b200 import RegionEHelper
-from regione_b200 import synthetic as syn
+from standins import synthetic as syn
 
 pipe = syn.build_pipeline(syn.FLUX_KONTEXT, seed=110, device="cuda")
 print("rho_target cache_thr edited schedule img_per_s ms_image full_ms region_ms")

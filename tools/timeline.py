@@ -11,9 +11,10 @@ ap.add_argument("--edited", type=int, default=1064)
 args = ap.parse_args()
 dump = tempfile.mktemp(suffix=".txt")
 os.environ["RGE_PROFILE_DUMP"] = dump
-from regione_b200 import _lib, synthetic as syn
+from regione_b200 import _lib
+from standins import synthetic as syn
 from regione_b200.engine import FluxEngine
-from regione_b200.standin import latent_image_ids
+from regione_b200.schedule import latent_image_ids
 
 dev = "cuda"
 lib = _lib.load()
