@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libregione_b200.so")
-SOURCES = ["gemm.cu", "gemm2.cu", "attention.cu", "elementwise.cu", "api.cu"]
+SOURCES = ["gemm.cu", "gemm2.cu", "attention.cu", "attention64.cu", "elementwise.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -40,6 +40,7 @@ constexpr int kHalfBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled half
 constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kSlots = 5;
 constexpr int kSmemBytes = 2 * kTileBytes + kSlots * kTileBytes + 256 + 1024;
+constexpr int kDefaultKernel = 0;       // 0: this file, 1: attention64.cu (RGE_ATTN_KERNEL overrides)
 constexpr int kDefaultPoly = 0;         // exponential pairs of every 8 on the FMA pipe (RGE_ATTN_POLY overrides)
 constexpr uint32_t kColS = 0, kColO = 256;  // TMEM column bases: S_i at kColS + 128 i, O_i at kColO + 128 i
 
@@ -360,7 +361,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
 }  // namespace
 
-cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
+cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
   if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
   // tuning knob attn_poly / RGE_ATTN_POLY: 0 (default, fastest measured), 2, 3 or 4 of every 8 exponential pairs on the
@@ -392,6 +393,12 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
   table[poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  int k = tuning().attn_kernel;
+  if (k < 0) k = kDefaultKernel;
+  return k == 1 ? launch_attention64(a, stream) : launch_attention128(a, stream);
 }
 
 }  // namespace rge

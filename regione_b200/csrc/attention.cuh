@@ -18,6 +18,10 @@ struct AttnArgs {
   float scale = 0.08838834764831845f;  // 1/sqrt(128)
 };
 
+// Dispatches on tuning().attn_kernel: 0 = attention.cu (128-row K/V tiles, P aliased onto S), 1 = attention64.cu
+// (64-row K/V tiles, P in TMEM columns of its own: Q K^T of the next tile overlaps the softmax of the current one).
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream);
+cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream);
+cudaError_t launch_attention64(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace rge

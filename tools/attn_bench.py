@@ -33,7 +33,7 @@ def sustained(fn, seconds):
 
 def main():
     secs = 0.5 if "--quick" in sys.argv else 1.2
-    shapes = [(8704, 8704), (1576, 8704), (4864, 4864)]
+    shapes = [(8704, 8704), (1576, 8704), (872, 8704), (4864, 4864)]
     for Sq, Skv in shapes:
         q = torch.randn(Sq, H * 128, device="cuda").bfloat16()
         k = torch.randn(Skv, H * 128, device="cuda").bfloat16()
@@ -45,6 +45,11 @@ def main():
             ops.set_option("attn_poly", poly)
             res[f"ours poly={poly}"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         ops.set_option("attn_poly", -1)
+        for kern in (0, 1):
+            ops.set_option("attn_kernel", kern)
+            res[f"ours kernel={'attention64' if kern else 'attention128'}"] = sustained(
+                lambda: ops.attention(q, k, v, H, out=o), secs)
+        ops.set_option("attn_kernel", -1)
         res["ours default"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         try:
             from flash_attn import flash_attn_func
