@@ -225,12 +225,12 @@ class FluxKontextPipeline:
     # prepare_latents and at inplace.py:398), on the CUDA library's pack kernels
     @staticmethod
     def _pack_latents(latents, batch_size=None, num_channels_latents=None, height=None, width=None):
-        from . import ops
+        from regione_b200 import ops
         return ops.pack_latents(latents)
 
     @staticmethod
     def _unpack_latents(latents, height, width, vae_scale_factor):
-        from . import ops
+        from regione_b200 import ops
         return ops.unpack_latents(latents, height, width, vae_scale_factor)
 
     @staticmethod
