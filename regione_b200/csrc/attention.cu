@@ -142,84 +142,97 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (all lanes loop, one elected lane issues)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
       for (int i = 0; i < 2; ++i)
         for (int half = 0; half < 2; ++half)
           tma_load_2d(s_q + i * kTileBytes + half * kHalfBytes, &map_q, q_full, head * 128 + half * 64,
                       q0 + i * kTile);
-      for (int t = 0; t < 2 * n_tiles; ++t) {
-        const int slot = t % kSlots;
-        const uint32_t ph = (t / kSlots) & 1;
-        mbar_wait(&kv_empty[slot], ph ^ 1);
+    }
+    __syncwarp();
+    for (int t = 0; t < 2 * n_tiles; ++t) {
+      const int slot = t % kSlots;
+      const uint32_t ph = (t / kSlots) & 1;
+      mbar_wait(&kv_empty[slot], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
         const CUtensorMap* map = (t & 1) ? &map_v : &map_k;
         for (int half = 0; half < 2; ++half)
           tma_load_2d(s_kv + slot * kTileBytes + half * kHalfBytes, map, &kv_full[slot], head * 128 + half * 64,
                       (t >> 1) * kTile);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
-      const uint32_t sq_addr = smem_u32(s_q);
-      const uint32_t skv_addr = smem_u32(s_kv);
-      auto slot_addr = [&](int t) { return skv_addr + (t % kSlots) * kTileBytes; };
-      auto wait_kv = [&](int t) {
-        mbar_wait(&kv_full[t % kSlots], (t / kSlots) & 1);
-        tc_fence_after();
-      };
-      // S_i = Q_i K^T : contraction over d, 8 steps of 16; both operands K-major, 128B-swizzled
-      auto issue_qk = [&](int i, uint32_t k_addr) {
+    // ------------------------------------------------------------ MMA issuer. The WHOLE warp runs the (warp-uniform)
+    // control flow and one elected lane issues: inside a divergent `if (lane == 0)` region ptxas wraps every tcgen05
+    // instruction in an ELECT / BRA.U.ANY loop and routes its operands through R2UR moves (~12 issue slots per MMA) -
+    // ~400 issue slots per K/V tile sitting in the serial  P ready -> P V -> Q K^T -> S ready  chain.
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+    const uint32_t sq_addr = smem_u32(s_q);
+    const uint32_t skv_addr = smem_u32(s_kv);
+    const uint64_t q_desc[2] = {make_sdesc_sw128(sq_addr, 0, 1024), make_sdesc_sw128(sq_addr + kTileBytes, 0, 1024)};
+    const uint64_t k_desc0 = make_sdesc_sw128(skv_addr, 0, 1024);            // + (slot offset >> 4)
+    const uint64_t v_desc0 = make_sdesc_sw128(skv_addr, kHalfBytes, 1024);   // V: MN-major, d atoms 16 KB apart
+    auto slot_off = [&](int t) { return (uint64_t)(((t % kSlots) * kTileBytes) >> 4); };
+    auto wait_kv = [&](int t) {
+      mbar_wait(&kv_full[t % kSlots], (t / kSlots) & 1);
+      tc_fence_after();
+    };
+    // S_i = Q_i K^T : contraction over d, 8 steps of 16; both operands K-major, 128B-swizzled
+    auto issue_qk = [&](int i, int t, uint64_t* release) {
+      if (elect_one()) {
+        const uint64_t kd = k_desc0 + slot_off(t);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-          umma_ss(tmem + kColS + i * 128, make_sdesc_sw128(sq_addr + i * kTileBytes + off, 0, 1024),
-                  make_sdesc_sw128(k_addr + off, 0, 1024), idesc_qk, kk != 0);
+          const uint32_t off = ((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4;
+          umma_ss(tmem + kColS + i * 128, q_desc[i] + off, kd + off, idesc_qk, kk != 0);
         }
         tc_commit(&s_full[i]);
-      };
-      // O_i += P_i V : contraction over kv, 8 steps of 16 rows (2048 B); V is [kv][d] = MN-major B with two
-      // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO)
-      // issued in two halves of 64 kv rows: the first starts while the softmax group still exponentiates the second
-      auto issue_pv = [&](int i, uint32_t v_addr, bool accumulate, int j) {
+        if (release) tc_commit(release);
+      }
+      __syncwarp();
+    };
+    // O_i += P_i V : contraction over kv, 8 steps of 16 rows (2048 B); V is [kv][d] = MN-major B with two
+    // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO)
+    // issued in two halves of 64 kv rows: the first starts while the softmax group still exponentiates the second
+    auto issue_pv = [&](int i, int t, uint32_t accumulate, int j, uint64_t* release) {
+      const uint64_t vd = v_desc0 + slot_off(t);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          mbar_wait(&p_half[2 * i + half], j & 1);
-          tc_fence_after();
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&p_half[2 * i + half], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 4 * half; kk < 4 * half + 4; ++kk) {
-            umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8,
-                    make_sdesc_sw128(v_addr + kk * 2048, kHalfBytes, 1024), idesc_pv, accumulate || kk != 0);
+            umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8, vd + ((kk * 2048) >> 4), idesc_pv,
+                    accumulate | (kk != 0));
+          }
+          if (half == 1) {
+            tc_commit(&o_bar[i]);
+            if (release) tc_commit(release);
           }
         }
-      };
-      mbar_wait(q_full, 0);
-      wait_kv(0);
-      issue_qk(0, slot_addr(0));
-      issue_qk(1, slot_addr(0));
-      tc_commit(&kv_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int tv = 2 * j + 1, tk = 2 * j + 2;
-        const bool more = j + 1 < n_tiles;
-        wait_kv(tv);
-        issue_pv(0, slot_addr(tv), j > 0, j);
-        tc_commit(&o_bar[0]);
-        if (more) {
-          wait_kv(tk);
-          issue_qk(0, slot_addr(tk));
-        }
-        issue_pv(1, slot_addr(tv), j > 0, j);
-        tc_commit(&o_bar[1]);
-        tc_commit(&kv_empty[tv % kSlots]);
-        if (more) {
-          issue_qk(1, slot_addr(tk));
-          tc_commit(&kv_empty[tk % kSlots]);
-        }
+        __syncwarp();
       }
+    };
+    mbar_wait(q_full, 0);
+    wait_kv(0);
+    issue_qk(0, 0, nullptr);
+    issue_qk(1, 0, &kv_empty[0]);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int tv = 2 * j + 1, tk = 2 * j + 2;
+      const bool more = j + 1 < n_tiles;
+      wait_kv(tv);
+      issue_pv(0, tv, j > 0, j, nullptr);
+      if (more) {
+        wait_kv(tk);
+        issue_qk(0, tk, nullptr);
+      }
+      issue_pv(1, tv, j > 0, j, &kv_empty[tv % kSlots]);
+      if (more) issue_qk(1, tk, &kv_empty[tk % kSlots]);
     }
   }
   } else {

@@ -122,32 +122,41 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 0) {
-      // ------------------------------------------------------------ TMA producer
-      if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (all lanes loop, one elected lane issues)
+      if (elect_one()) {
         mbar_arrive_expect_tx(q_full, 2 * kQTileBytes);
         for (int i = 0; i < 2; ++i)
           for (int half = 0; half < 2; ++half)
             tma_load_2d(s_q + i * kQTileBytes + half * kQHalfBytes, &map_q, q_full, head * 128 + half * 64,
                         q0 + i * kQTile);
-        for (int t = 0; t < 2 * n_tiles; ++t) {   // ring order K_0, V_0, K_1, V_1, ...
-          const int slot = t % kSlots;
-          const uint32_t ph = (t / kSlots) & 1;
-          mbar_wait(&kv_empty[slot], ph ^ 1);
+      }
+      __syncwarp();
+      for (int t = 0; t < 2 * n_tiles; ++t) {   // ring order K_0, V_0, K_1, V_1, ...
+        const int slot = t % kSlots;
+        const uint32_t ph = (t / kSlots) & 1;
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[slot], kKVTileBytes);
           const CUtensorMap* map = (t & 1) ? &map_v : &map_k;
           for (int half = 0; half < 2; ++half)
             tma_load_2d(s_kv + slot * kKVTileBytes + half * kKVHalfBytes, map, &kv_full[slot], head * 128 + half * 64,
                         (t >> 1) * kKV);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      // ------------------------------------------------------------ MMA issuer: whatever is ready, in tile order per group
-      if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer: whatever is ready, in tile order per group.
+      // The WHOLE warp runs the (warp-uniform) control flow and one elected lane issues: inside a divergent
+      // `if (lane == 0)` region ptxas wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop and routes its
+      // operands through R2UR moves (~12 issue slots per MMA), which made this thread the bottleneck of the kernel.
+      {
         constexpr uint32_t idesc_qk = make_idesc_bf16(128, kKV, 0, 0);
         constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
         const uint32_t sq_addr = smem_u32(s_q);
         const uint32_t skv_addr = smem_u32(s_kv);
-        auto slot_addr = [&](int t) { return skv_addr + (t % kSlots) * kKVTileBytes; };
+        const uint64_t q_desc[2] = {make_sdesc_sw128(sq_addr, 0, 1024), make_sdesc_sw128(sq_addr + kQTileBytes, 0, 1024)};
+        const uint64_t k_desc0 = make_sdesc_sw128(skv_addr, 0, 1024);
+        const uint64_t v_desc0 = make_sdesc_sw128(skv_addr, kKVHalfBytes, 1024);
         auto kv_ready = [&](int t) { return mbar_test(&kv_full[t % kSlots], (t / kSlots) & 1); };
         int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
         mbar_wait(q_full, 0);
@@ -161,16 +170,18 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             int j = qk_next[i];
             if (j < n_tiles && (j == 0 || mbar_test(&s_free[i], (j - 1) & 1)) && kv_ready(2 * j)) {
               tc_fence_after();
-              const uint32_t k_addr = slot_addr(2 * j);
+              const uint64_t kd = k_desc0 + (uint64_t)((((2 * j) % kSlots) * kKVTileBytes) >> 4);
+              const bool release = qk_next[i ^ 1] > j;   // both groups have used K_j
+              if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                umma_ss(tmem + kColS + i * kKV,
-                        make_sdesc_sw128(sq_addr + i * kQTileBytes + (kk >> 2) * kQHalfBytes + (kk & 3) * 32, 0, 1024),
-                        make_sdesc_sw128(k_addr + (kk >> 2) * kKVHalfBytes + (kk & 3) * 32, 0, 1024), idesc_qk,
-                        kk != 0);
+                for (int kk = 0; kk < 8; ++kk) {
+                  umma_ss(tmem + kColS + i * kKV, q_desc[i] + (((kk >> 2) * kQHalfBytes + (kk & 3) * 32) >> 4),
+                          kd + (((kk >> 2) * kKVHalfBytes + (kk & 3) * 32) >> 4), idesc_qk, kk != 0);
+                }
+                tc_commit(&s_full[i]);
+                if (release) tc_commit(&kv_empty[(2 * j) % kSlots]);
               }
-              tc_commit(&s_full[i]);
-              if (qk_next[i ^ 1] > j) tc_commit(&kv_empty[(2 * j) % kSlots]);   // both groups have used K_j
+              __syncwarp();
               ++qk_next[i];
               progressed = true;
             }
@@ -179,14 +190,19 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             j = pv_next[i];
             if (j < n_tiles && mbar_test(&p_full[i], j & 1) && kv_ready(2 * j + 1)) {
               tc_fence_after();
-              const uint32_t v_addr = slot_addr(2 * j + 1);
+              const uint64_t vd = v_desc0 + (uint64_t)((((2 * j + 1) % kSlots) * kKVTileBytes) >> 4);
+              const bool release = pv_next[i ^ 1] > j;   // both groups have used V_j
+              const uint32_t acc = j > 0;
+              if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < kKV / 16; ++kk) {
-                umma_ts(tmem + kColO + i * 128, tmem + kColP + i * (kKV / 2) + kk * 8,
-                        make_sdesc_sw128(v_addr + kk * 2048, kKVHalfBytes, 1024), idesc_pv, j > 0 || kk != 0);
+                for (int kk = 0; kk < kKV / 16; ++kk) {
+                  umma_ts(tmem + kColO + i * 128, tmem + kColP + i * (kKV / 2) + kk * 8, vd + ((kk * 2048) >> 4), idesc_pv,
+                          acc | (kk != 0));
+                }
+                tc_commit(&o_bar[i]);
+                if (release) tc_commit(&kv_empty[(2 * j + 1) % kSlots]);
               }
-              tc_commit(&o_bar[i]);
-              if (pv_next[i ^ 1] > j) tc_commit(&kv_empty[(2 * j + 1) % kSlots]);   // both groups have used V_j
+              __syncwarp();
               ++pv_next[i];
               progressed = true;
             }

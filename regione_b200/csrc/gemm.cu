@@ -85,53 +85,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
 
+  // The producer and issuer warps run their (warp-uniform) loops with ALL lanes and elect one lane per asynchronous
+  // instruction group. Inside a divergent `if (lane == 0)` region ptxas wraps every UTMALDG / UTCHMMA / UTCBAR in an
+  // ELECT + BRA.U.ANY loop and routes the operands through R2UR moves: ~75 issue slots per k-block, i.e. 250-350 cycles
+  // for a single thread - more than the 128-256 cycles the tensor pipe needs for a k-block of a 128 x (128-256) tile.
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
           tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * bn);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, bn, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t use = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], use ^ 1);
+    // ------------------------------------------------------------ MMA issuer (one elected lane)
+    const uint32_t idesc = make_idesc_bf16(BM, bn, 0, 0);
+    const uint64_t desc0 = make_sdesc_sw128(smem_u32(smem), 0, 1024);   // + (byte offset >> 4) per stage / operand
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], use ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t a_desc = make_sdesc_sw128(sa, 0, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(sb, 0, 1024);
+        if (elect_one()) {
+          const uint64_t a_desc = desc0 + (uint64_t)((stage * stage_bytes) >> 4);
+          const uint64_t b_desc = a_desc + (kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4)
             umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);
         }
-        tc_commit(&tfull_bar[acc]);
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -231,54 +236,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_group_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const GroupTile t = group_decode(g, tile);
-        const int bn = g.bn[t.prob];
-        const int num_kb = (g.p[t.prob].K + BK - 1) / BK;
-        const uint32_t bytes = kABytes + bn * BK * 2;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------------------ TMA producer (all lanes loop, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const GroupTile t = group_decode(g, tile);
+      const int bn = g.bn[t.prob];
+      const int num_kb = (g.p[t.prob].K + BK - 1) / BK;
+      const uint32_t bytes = kABytes + bn * BK * 2;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
           tma_load_2d(sa, &g.map_a[t.prob], &full_bar[stage], kb * BK, t.m_blk * BM);
           tma_load_2d(sb, &g.map_b[t.prob], &full_bar[stage], kb * BK, t.n_blk * bn);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const GroupTile t = group_decode(g, tile);
-        const uint32_t idesc = make_idesc_bf16(BM, g.bn[t.prob], 0, 0);
-        const int num_kb = (g.p[t.prob].K + BK - 1) / BK;
-        const int acc = it & 1;
-        const uint32_t use = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], use ^ 1);
+    // ------------------------------------------------------------ MMA issuer (one elected lane)
+    const uint64_t desc0 = make_sdesc_sw128(smem_u32(smem), 0, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const GroupTile t = group_decode(g, tile);
+      const uint32_t idesc = make_idesc_bf16(BM, g.bn[t.prob], 0, 0);
+      const int num_kb = (g.p[t.prob].K + BK - 1) / BK;
+      const int acc = it & 1;
+      const uint32_t use = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], use ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kMaxBN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kMaxBN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t a_desc = make_sdesc_sw128(sa, 0, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(sb, 0, 1024);
+        if (elect_one()) {
+          const uint64_t a_desc = desc0 + (uint64_t)((stage * stage_bytes) >> 4);
+          const uint64_t b_desc = a_desc + (kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           tc_commit(&empty_bar[stage]);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);
         }
-        tc_commit(&tfull_bar[acc]);
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {

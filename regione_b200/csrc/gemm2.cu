@@ -70,29 +70,33 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
 
+  // Producer and issuer warps loop with all lanes and elect one lane per asynchronous instruction group (see gemm.cu:
+  // a divergent `if (lane == 0)` region costs ~75 issue slots per k-block in ELECT / BRA.U.ANY loops and R2UR moves).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
           else mbar_arrive_cluster(&full_bar[stage], 0);
           tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
           tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane)
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      const uint64_t desc0 = make_sdesc_sw128(smem_u32(smem), 0, 1024);   // + (byte offset >> 4) per stage / operand
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -105,17 +109,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t a_desc = make_sdesc_sw128(sa, 0, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(sb, 0, 1024);
+          if (elect_one()) {
+            const uint64_t a_desc = desc0 + (uint64_t)((stage * kStageBytes) >> 4);
+            const uint64_t b_desc = a_desc + (kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          tc_commit_pair(&empty_bar[stage], 3);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            tc_commit_pair(&empty_bar[stage], 3);
+            if (kb == num_kb - 1) tc_commit_pair(&tfull_bar[acc], 3);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(&tfull_bar[acc], 3);
       }
     }
   } else {

@@ -19,7 +19,6 @@ inline int current_device() {
 struct Tuning {
   int attn_poly;     // RGE_ATTN_POLY:   exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
   int attn_kernel;   // RGE_ATTN_KERNEL: 0 = attention.cu, 1 = attention64.cu (decoupled pipeline), -1 = default
-  int attn_split;    // RGE_ATTN_SPLIT:  KV splits of the attention grid, 0 = choose per launch
   int gemm_bn;       // RGE_GEMM_BN:     forced tile width of the 1-CTA GEMM, 0 = choose per launch
   int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never
   int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
@@ -37,7 +36,6 @@ inline Tuning& tuning() {
     Tuning x;
     x.attn_poly = env_int("RGE_ATTN_POLY", -1);
     x.attn_kernel = env_int("RGE_ATTN_KERNEL", -1);
-    x.attn_split = env_int("RGE_ATTN_SPLIT", 0);
     x.gemm_bn = env_int("RGE_GEMM_BN", 0);
     x.min_m_2cta = env_int("RGE_2CTA_MIN_M", 2048);
     const char* r = getenv("RGE_RASTER");
@@ -54,7 +52,6 @@ inline bool set_tuning(const char* name, int value) {
   Tuning& t = tuning();
   if (!strcmp(name, "attn_poly")) t.attn_poly = value;
   else if (!strcmp(name, "attn_kernel")) t.attn_kernel = value;
-  else if (!strcmp(name, "attn_split")) t.attn_split = value;
   else if (!strcmp(name, "gemm_bn")) t.gemm_bn = value;
   else if (!strcmp(name, "2cta_min_m")) t.min_m_2cta = value;
   else if (!strcmp(name, "raster")) t.raster = value;
