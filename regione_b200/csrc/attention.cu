@@ -42,6 +42,7 @@ constexpr int kSlots = 5;
 constexpr int kSmemBytes = 2 * kTileBytes + kSlots * kTileBytes + 256 + 1024;
 constexpr int kDefaultKernel = 0;       // 0: this file, 1: attention64.cu (RGE_ATTN_KERNEL overrides)
 constexpr int kDefaultPoly = 0;         // exponential pairs of every 8 on the FMA pipe (RGE_ATTN_POLY overrides)
+constexpr int kDefaultVariant = 0;      // MMA issue order / P granularity (RGE_ATTN_VARIANT overrides)
 constexpr uint32_t kColS = 0, kColO = 256;  // TMEM column bases: S_i at kColS + 128 i, O_i at kColO + 128 i
 
 struct AttnDev {
@@ -88,8 +89,45 @@ __device__ __forceinline__ constexpr bool poly_pair(int kPoly, int pair) {
        : kPoly == 2 ? (pair == 3 || pair == 7) : false;
 }
 
+// first kv position of part `part` of a P row published in `parts` pieces: halves, or 64 | 32 | 32
+__host__ __device__ constexpr int part_begin(int parts, int part) {
+  return parts == 2 ? 64 * part : (part == 0 ? 0 : 32 + 32 * part);
+}
+
+// scores [J0, J1) of the row: scale, shift, exponential, row-sum, packed bf16 into v[J0/2 .. J1/2)
+template <int kPoly, int J0, int J1>
+__device__ __forceinline__ void exp_block(uint32_t* v, uint64_t sl2_2, uint64_t neg_m2, uint64_t& sum_a,
+                                          uint64_t& sum_b) {
+#pragma unroll
+  for (int jj = J0; jj < J1; jj += 4) {
+    const uint64_t xa = fma2(pack2u(v[jj + 0], v[jj + 1]), sl2_2, neg_m2);
+    const uint64_t xb = fma2(pack2u(v[jj + 2], v[jj + 3]), sl2_2, neg_m2);
+    float p0, p1, p2, p3;
+    if (poly_pair(kPoly, (jj >> 1) & 7)) {
+      ex2_poly2(xa, p0, p1);
+    } else {
+      unpack2f(xa, p0, p1);
+      p0 = ex2(p0);
+      p1 = ex2(p1);
+    }
+    if (poly_pair(kPoly, ((jj >> 1) + 1) & 7)) {
+      ex2_poly2(xb, p2, p3);
+    } else {
+      unpack2f(xb, p2, p3);
+      p2 = ex2(p2);
+      p3 = ex2(p3);
+    }
+    sum_a = add2(sum_a, pack2f(p0, p1));
+    sum_b = add2(sum_b, pack2f(p2, p3));
+    v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
+    v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
+  }
+}
+
 // kPoly = how many of every eight score PAIRS use ex2_poly2 instead of MUFU.EX2 (0, 2, 3 or 4).
-template <int kPoly>
+// kEarlyQK: the upper 64 score columns of the next tile are issued before this tile's P exists (see the MMA issuer).
+// kParts: P is published in 2 halves or in 3 pieces (64 | 32 | 32 kv positions).
+template <int kPoly, bool kEarlyQK, int kParts>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnDev p) {
@@ -102,9 +140,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + kSlots;
   uint64_t* s_full = kv_empty + kSlots;
-  uint64_t* p_half = s_full + 2;   // [group][half]: P columns [64 half, 64 half + 64) of the group are in TMEM
-  uint64_t* o_bar = p_half + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
+  uint64_t* p_part = s_full + 2;   // [group][part]: this part of the group's P row is in TMEM (kParts per group)
+  uint64_t* o_bar = p_part + 6;
+  uint64_t* s_free = o_bar + 2;    // [group]: the group holds its score row in registers, columns 64.. may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,9 +162,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_half[2 * i], 4);
-      mbar_init(&p_half[2 * i + 1], 4);
+      for (int part = 0; part < 3; ++part) mbar_init(&p_part[3 * i + part], 4);
       mbar_init(&o_bar[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_mbar_init();
   }
@@ -195,22 +234,36 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
       __syncwarp();
     };
+    // One 64-column half of S_i (kv rows 64 part .. 64 part + 63 of the tile): N = 64, K rows 64.. start 8 swizzle atoms
+    // (8 KB) into each 64-wide d half of the tile.
+    constexpr uint32_t idesc_qk64 = make_idesc_bf16(128, 64, 0, 0);
+    auto issue_qk_half = [&](int i, int t, int part) {
+      if (elect_one()) {
+        const uint64_t kd = k_desc0 + slot_off(t) + (uint64_t)((part * 64 * 128) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = ((kk >> 2) * kHalfBytes + (kk & 3) * 32) >> 4;
+          umma_ss(tmem + kColS + i * 128 + part * 64, q_desc[i] + off, kd + off, idesc_qk64, kk != 0);
+        }
+      }
+      __syncwarp();
+    };
     // O_i += P_i V : contraction over kv, 8 steps of 16 rows (2048 B); V is [kv][d] = MN-major B with two
-    // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO)
-    // issued in two halves of 64 kv rows: the first starts while the softmax group still exponentiates the second
+    // 64-wide d atoms 16 KB apart (LBO) and 8-row groups 1 KB apart (SBO). Issued in kParts pieces as the softmax
+    // group publishes them, so only the last piece's MMAs sit behind the group's last exponential.
     auto issue_pv = [&](int i, int t, uint32_t accumulate, int j, uint64_t* release) {
       const uint64_t vd = v_desc0 + slot_off(t);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        mbar_wait(&p_half[2 * i + half], j & 1);
+      for (int part = 0; part < kParts; ++part) {
+        mbar_wait(&p_part[3 * i + part], j & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 4 * half; kk < 4 * half + 4; ++kk) {
+          for (int kk = part_begin(kParts, part) / 16; kk < part_begin(kParts, part + 1) / 16; ++kk) {
             umma_ts(tmem + kColO + i * 128, tmem + kColS + i * 128 + kk * 8, vd + ((kk * 2048) >> 4), idesc_pv,
                     accumulate | (kk != 0));
           }
-          if (half == 1) {
+          if (part == kParts - 1) {
             tc_commit(&o_bar[i]);
             if (release) tc_commit(release);
           }
@@ -222,17 +275,46 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     wait_kv(0);
     issue_qk(0, 0, nullptr);
     issue_qk(1, 0, &kv_empty[0]);
-    for (int j = 0; j < n_tiles; ++j) {
-      const int tv = 2 * j + 1, tk = 2 * j + 2;
-      const bool more = j + 1 < n_tiles;
-      wait_kv(tv);
-      issue_pv(0, tv, j > 0, j, nullptr);
-      if (more) {
-        wait_kv(tk);
-        issue_qk(0, tk, nullptr);
+    if constexpr (!kEarlyQK) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int tv = 2 * j + 1, tk = 2 * j + 2;
+        const bool more = j + 1 < n_tiles;
+        wait_kv(tv);
+        issue_pv(0, tv, j > 0, j, nullptr);
+        if (more) {
+          wait_kv(tk);
+          issue_qk(0, tk, nullptr);
+        }
+        issue_pv(1, tv, j > 0, j, &kv_empty[tv % kSlots]);
+        if (more) issue_qk(1, tk, &kv_empty[tk % kSlots]);
       }
-      issue_pv(1, tv, j > 0, j, &kv_empty[tv % kSlots]);
-      if (more) issue_qk(1, tk, &kv_empty[tk % kSlots]);
+    } else {
+      // P_i(j) only occupies columns [0, 64) of S_i: the upper half of S_i(j+1) is issued as soon as the group holds
+      // S_i(j) in registers (`s_free`), long before P_i(j) exists; after P_i V_j only the lower half (256 instead of
+      // 512 tensor cycles) remains in the serial  P ready -> P V -> Q K^T -> S ready  chain.
+      for (int j = 0; j < n_tiles; ++j) {
+        const int tv = 2 * j + 1, tk = 2 * j + 2;
+        const bool more = j + 1 < n_tiles;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (more) {
+            mbar_wait(&s_free[i], j & 1);
+            tc_fence_after();
+            if (i == 0) wait_kv(tk);
+            issue_qk_half(i, tk, 1);
+          }
+          if (i == 0) wait_kv(tv);
+          issue_pv(i, tv, j > 0, j, i == 1 ? &kv_empty[tv % kSlots] : nullptr);
+          if (more) {
+            issue_qk_half(i, tk, 0);
+            if (elect_one()) {
+              tc_commit(&s_full[i]);
+              if (i == 1) tc_commit(&kv_empty[tk % kSlots]);
+            }
+            __syncwarp();
+          }
+        }
+      }
     }
   }
   } else {
@@ -258,6 +340,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       tmem_ld32p(t_s + 64, v + 64);
       tmem_ld32p(t_s + 96, v + 96);
       tmem_ld_wait();
+      if constexpr (kEarlyQK) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[grp]);
+      }
       if (n_valid < kTile) {  // KV tail (last tile only): masked columns behave as -inf
 #pragma unroll
         for (int jj = 0; jj < 128; ++jj)
@@ -303,38 +390,30 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const float neg_m = -m_run * sl2;
       const uint64_t neg_m2 = pack2f(neg_m, neg_m);
       uint64_t sum_a = pack2f(0.f, 0.f), sum_b = sum_a;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int jj = 64 * half; jj < 64 * half + 64; jj += 4) {
-          const uint64_t xa = fma2(pack2u(v[jj + 0], v[jj + 1]), sl2_2, neg_m2);
-          const uint64_t xb = fma2(pack2u(v[jj + 2], v[jj + 3]), sl2_2, neg_m2);
-          float p0, p1, p2, p3;
-          if (poly_pair(kPoly, (jj >> 1) & 7)) {
-            ex2_poly2(xa, p0, p1);
-          } else {
-            unpack2f(xa, p0, p1);
-            p0 = ex2(p0);
-            p1 = ex2(p1);
-          }
-          if (poly_pair(kPoly, ((jj >> 1) + 1) & 7)) {
-            ex2_poly2(xb, p2, p3);
-          } else {
-            unpack2f(xb, p2, p3);
-            p2 = ex2(p2);
-            p3 = ex2(p3);
-          }
-          sum_a = add2(sum_a, pack2f(p0, p1));
-          sum_b = add2(sum_b, pack2f(p2, p3));
-          v[(jj >> 1) + 0] = pack_bf16x2(p0, p1);   // in place: slot jj/2 <= jj has already been consumed
-          v[(jj >> 1) + 1] = pack_bf16x2(p2, p3);
-        }
-        // publish this half of P (32 TMEM columns = 64 kv positions) so its PV MMAs can start
-        tmem_st32p(t_s + 32 * half, v + 32 * half);
+      // publish one piece of P so that its PV MMAs can start
+      auto publish = [&](int part) {
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_half[2 * grp + half]);
+        if (lane == 0) mbar_arrive(&p_part[3 * grp + part]);
+      };
+      if constexpr (kParts == 2) {
+        exp_block<kPoly, 0, 64>(v, sl2_2, neg_m2, sum_a, sum_b);
+        tmem_st32p(t_s, v);
+        publish(0);
+        exp_block<kPoly, 64, 128>(v, sl2_2, neg_m2, sum_a, sum_b);
+        tmem_st32p(t_s + 32, v + 32);
+        publish(1);
+      } else {
+        exp_block<kPoly, 0, 64>(v, sl2_2, neg_m2, sum_a, sum_b);
+        tmem_st32p(t_s, v);
+        publish(0);
+        exp_block<kPoly, 64, 96>(v, sl2_2, neg_m2, sum_a, sum_b);
+        tmem_st16(t_s + 32, v + 32);
+        publish(1);
+        exp_block<kPoly, 96, 128>(v, sl2_2, neg_m2, sum_a, sum_b);
+        tmem_st16(t_s + 48, v + 48);
+        publish(2);
       }
       float sum0, sum1, sum2, sum3;
       unpack2f(sum_a, sum0, sum1);
@@ -377,17 +456,24 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
   if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
-  // tuning knob attn_poly / RGE_ATTN_POLY: 0 (default, fastest measured), 2, 3 or 4 of every 8 exponential pairs on the
-  // FMA pipe instead of MUFU
+  // tuning knobs: attn_poly / RGE_ATTN_POLY = 0, 2, 3 or 4 of every 8 exponential pairs on the FMA pipe instead of
+  // MUFU; attn_variant / RGE_ATTN_VARIANT = 0 (whole Q K^T after P V, P in halves), 1 (early upper half of Q K^T),
+  // 2 (early upper half, P in 64 | 32 | 32 pieces)
   int poly = tuning().attn_poly;
   if (poly < 0) poly = kDefaultPoly;
   if (poly != 2 && poly != 3 && poly != 4) poly = 0;
+  int var = tuning().attn_variant;
+  if (var < 0 || var > 2) var = kDefaultVariant;
   typedef void (*Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
-  static const Kernel table[4] = {attention_kernel<0>, attention_kernel<2>, attention_kernel<3>, attention_kernel<4>};
+  static const Kernel table[12] = {
+      attention_kernel<0, false, 2>, attention_kernel<2, false, 2>, attention_kernel<3, false, 2>,
+      attention_kernel<4, false, 2>, attention_kernel<0, true, 2>,  attention_kernel<2, true, 2>,
+      attention_kernel<3, true, 2>,  attention_kernel<4, true, 2>,  attention_kernel<0, true, 3>,
+      attention_kernel<2, true, 3>,  attention_kernel<3, true, 3>,  attention_kernel<4, true, 3>};
   const int dev = current_device();
   static bool attr_set[kMaxDevices] = {};   // per device: a process may drive several GPUs
   if (!attr_set[dev]) {
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 12; ++k) {
       cudaError_t e = cudaFuncSetAttribute(table[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return e;
     }
@@ -404,7 +490,7 @@ cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   p.Skv = a.Skv;
   p.sl2 = a.scale * 1.4426950408889634f;
   dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
-  table[poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  table[4 * var + (poly == 0 ? 0 : poly - 1)]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
 

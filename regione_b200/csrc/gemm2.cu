@@ -1,8 +1,14 @@
 // 2-CTA (cluster of two, tcgen05 cta_group::2) variant of the persistent bf16 GEMM for the large-M launches of a FULL
-// step: one 256 x 256 output tile per CTA pair. Each CTA stages its own 128 rows of A and its own 128 rows (half of
-// N) of W, the leader CTA's single MMA thread issues M=256 N=256 K=16 instructions that read both halves, and each
-// CTA's TMEM receives the 128 x 256 accumulator of its M half. Compared with the 1-CTA kernel this halves the
-// shared-memory operand traffic per FLOP and leaves room for a 6-stage ring (32 KB per stage per CTA).
+// step: one 256 x bn output tile per CTA pair (bn <= 256). Each CTA stages its own 128 rows of A and its own bn / 2
+// rows (half of the tile's N) of W, the leader CTA's single MMA thread issues M=256 N=bn K=16 instructions that read
+// both halves, and each CTA's TMEM receives the 128 x bn accumulator of its M half. Compared with the 1-CTA kernel this
+// halves the shared-memory operand traffic per FLOP and leaves room for a 6-stage ring (32 KB per stage per CTA).
+//
+// The tile width is a launch parameter (any multiple of 16): with 74 pairs, 256-wide tiles leave the last wave of the
+// hot shapes half empty (8704 x 3072: 408 tiles = 5.51 waves, 8192 x 3072: 384 tiles = 5.19 waves - and measured
+// throughput is exactly the tail-free rate x waves / ceil(waves)); the host picks the width that minimises
+// ceil(waves) x width (pick_bn2: 240 resp. 192 for those two shapes). A narrower tile changes neither the k-order of
+// any output element's sum nor its epilogue, so results stay bit-identical.
 //
 //   warp 0      TMA producer (both CTAs; transaction bytes are credited to the leader's `full` barrier)
 //   warp 1      MMA issuer   (leader CTA only) / TMEM allocation (both CTAs, cta_group::2)
@@ -15,7 +21,7 @@ namespace rge {
 namespace {
 
 constexpr int BM = 128;   // rows per CTA (256 per pair)
-constexpr int BN = 256;   // columns per pair (128 rows of W staged per CTA)
+constexpr int BN = 256;   // widest tile: columns per pair (128 rows of W staged per CTA), TMEM accumulator stride
 constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr int kStages = 6;
@@ -27,7 +33,8 @@ constexpr int kTmemCols = 512;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmDev p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmDev p,
+             const int bn) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -64,7 +71,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
-  const int num_n = (p.N + BN - 1) / BN;
+  const int num_n = (p.N + bn - 1) / bn;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
   const int pair = blockIdx.x >> 1;
@@ -83,10 +90,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (elect_one()) {
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + (bn / 2) * BK * 2));
           else mbar_arrive_cluster(&full_bar[stage], 0);
           tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, m_blk * 2 * BM + (int)rank * BM);
-          tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * BK, n_blk * bn + (int)rank * (bn / 2));
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -95,7 +102,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane)
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(2 * BM, bn, 0, 0);
       const uint64_t desc0 = make_sdesc_sw128(smem_u32(smem), 0, 1024);   // + (byte offset >> 4) per stage / operand
       int stage = 0;
       uint32_t phase = 0;
@@ -135,7 +142,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      gemm_epilogue_row<EPI>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * BN, BN);
+      gemm_epilogue_row<EPI>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * bn, bn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
@@ -147,6 +154,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
+// Tile width: minimise  ceil(tiles / pairs) x (bn + 4)  over the multiples of 16 (of 128 for EPI_NORM_ROPE, whose
+// epilogue owns whole heads); the small constant stands for the per-tile pipeline drain and breaks ties towards the
+// wider tile. RGE_GEMM2_BN / "gemm2_bn" forces a width (256 = the fixed tile of the earlier kernel).
+int pick_bn2(const GemmArgs& a, int pairs) {
+  const bool heads = a.epilogue == EPI_NORM_ROPE;
+  const int forced = tuning().gemm2_bn;
+  if (forced >= 16 && forced <= BN && forced % (heads ? 128 : 16) == 0) return forced;
+  const long num_m = (a.M + 2 * BM - 1) / (2 * BM);
+  int best = BN;
+  long best_cost = 0;
+  for (int bn = BN; bn >= 128; bn -= heads ? 128 : 16) {
+    const long tiles = num_m * ((a.N + bn - 1) / bn);
+    const long cost = ((tiles + pairs - 1) / pairs) * (bn + 4);
+    if (bn == BN || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
 template <int EPI>
 cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   static bool attr_set[kMaxDevices] = {};   // per device
@@ -156,22 +181,23 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
+  const int max_pairs = num_sms / 2;
+  const int bn = pick_bn2(a, max_pairs);
   CUtensorMap map_a, map_b;
   if (!make_tmap_bf16_2d(&map_a, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, BN / 2)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, bn / 2)) return cudaErrorInvalidValue;
   GemmDev p = to_dev(a);
   p.n_fast = pick_n_fast(a);
-  const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + BN - 1) / BN);
-  const int max_pairs = num_sms / 2;
+  const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + bn - 1) / bn);
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  gemm2_kernel<EPI><<<2 * pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p);
+  gemm2_kernel<EPI><<<2 * pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, bn);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_gemm_2cta(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  if (a.N % BN) return cudaErrorNotSupported;
+  if (a.N % 16) return cudaErrorNotSupported;
   switch (a.epilogue) {
     case EPI_STORE: return launch_t<EPI_STORE>(a, num_sms, stream);
     case EPI_GELU: return launch_t<EPI_GELU>(a, num_sms, stream);

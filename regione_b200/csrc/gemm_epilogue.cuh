@@ -69,14 +69,15 @@ __device__ __forceinline__ void ld_vec8(const __nv_bfloat16* ptr, float (&f)[8])
 // (`accumulator.to(tl.float16)`, RegionE/FluxKontext/fused_kernels.py:80); only with RGE_GEMM_FP16_ROUNDTRIP.
 __device__ __forceinline__ float fp16_roundtrip(float x) { return __half2float(__float2half_rn(x)); }
 
-// One 32-column chunk of the STORE / GELU / GATE_RES epilogues: v = accumulator columns [n0, n0 + 32) of this thread's
-// row, rv = the residual row's same columns (GATE_RES only).
-template <int EPI>
+// One chunk of NG x 8 columns (32, or 16 for the tail of a tile whose width is not a multiple of 32) of the STORE /
+// GELU / GATE_RES epilogues: v = accumulator columns [n0, n0 + 8 NG) of this thread's row, rv = the residual row's same
+// columns (GATE_RES only).
+template <int EPI, int NG = 4>
 __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&v)[32], const uint4 (&rv)[4],
                                                __nv_bfloat16* out_ptr, int n0, bool valid) {
   uint32_t o[16];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NG; ++g) {
     float b[8], gt[8];
     if (p.bias) ld_vec8(p.bias + n0 + 8 * g, b);
     if constexpr (EPI == EPI_GATE_RES) ld_vec8(p.gate + n0 + 8 * g, gt);
@@ -105,17 +106,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
   if (valid) {
     uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+    for (int t = 0; t < NG; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
   }
 }
 
-template <int EPI>
+template <int EPI, int NG = 4>
 __device__ __forceinline__ void load_residual(const GemmDev& p, uint4 (&rv)[4], int m, int n0, bool valid) {
   if constexpr (EPI == EPI_GATE_RES) {
     if (valid) {
       const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long)m * p.ldr + n0);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) rv[t] = rp[t];
+      for (int t = 0; t < NG; ++t) rv[t] = rp[t];
+#pragma unroll
+      for (int t = NG; t < 4; ++t) rv[t] = make_uint4(0, 0, 0, 0);
       return;
     }
   }
@@ -124,7 +127,7 @@ __device__ __forceinline__ void load_residual(const GemmDev& p, uint4 (&rv)[4], 
 }
 
 // taddr: TMEM address of this thread's row (lane field set) at column 0 of the accumulator; m: global row;
-// n_base: first global column of the tile; bn: tile width (multiple of 32; of 128 for EPI_NORM_ROPE). All 32 lanes of
+// n_base: first global column of the tile; bn: tile width (multiple of 16; of 128 for EPI_NORM_ROPE). All 32 lanes of
 // the warp must call this together.
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t taddr, int m, int n_base, int bn) {
@@ -206,13 +209,16 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
   } else {
     // software pipeline over 32-column chunks: the TMEM load (and, for GATE_RES, the residual-row loads, whose L2 /
     // DRAM latency one thread per row cannot hide otherwise) of chunk c + 1 are in flight while chunk c is processed
-    int n_chunks = (p.N - n_base) / 32;
-    if (n_chunks > bn / 32) n_chunks = bn / 32;
-    if (n_chunks <= 0) return;
+    int cols = p.N - n_base;
+    if (cols > bn) cols = bn;
+    const int n_chunks = cols / 32;
+    const bool tail16 = (cols & 16) != 0;   // tile widths are multiples of 16 (CTA-pair kernel: 240, 208, 176, ...)
     uint32_t va[32], vb[32];
     uint4 ra[4], rb[4];
-    tmem_ld32(taddr, va);
-    load_residual<EPI>(p, ra, m, n_base, valid);
+    if (n_chunks > 0) {
+      tmem_ld32(taddr, va);
+      load_residual<EPI>(p, ra, m, n_base, valid);
+    }
 #pragma unroll 1
     for (int c = 0; c < n_chunks; c += 2) {
       tmem_ld_wait();
@@ -229,6 +235,12 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
         }
         epilogue_chunk<EPI>(p, vb, rb, out_ptr, n_base + (c + 1) * 32, valid);
       }
+    }
+    if (tail16) {
+      tmem_ld16p(taddr + n_chunks * 32, va);
+      load_residual<EPI, 2>(p, ra, m, n_base + n_chunks * 32, valid);
+      tmem_ld_wait();
+      epilogue_chunk<EPI, 2>(p, va, ra, out_ptr, n_base + n_chunks * 32, valid);
     }
   }
 }

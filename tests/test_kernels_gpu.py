@@ -75,6 +75,47 @@ def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
         assert rel_l2(q, x.transpose(1, 2).reshape(M, N)) <= BF16_TOL
 
 
+@pytest.mark.parametrize("bn", [240, 208, 192, 176, 144, 128])
+def test_gemm_cta_pair_kernel_tile_widths_bit_identical(bn):
+    """The CTA-pair kernel's tile width is a launch parameter (any multiple of 16, chosen per shape to fill the last
+    wave of the 74 pairs): ragged M, a ragged last N tile and the 16-column tail chunk of the epilogue. A narrower tile
+    changes neither the k-order of any element's sum nor its epilogue: every width is BIT-identical to the 256-wide
+    tile, for every epilogue that allows it."""
+    from regione_b200 import _lib, ops
+    g = _gen(22)
+    M, N, K = 2304 + 77, 3072, 192
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    gate = torch.randn(N, device="cuda", generator=g).bfloat16()
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    rows = torch.randperm(M + 100, device="cuda", generator=g)[:M].int()
+
+    def run_all():
+        outs = [ops.gemm(a, w, b), ops.gemm(a, w, b, epilogue=_lib.EPI_GELU)]
+        o = res.clone()
+        ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, gate=gate, res=o, out=o)
+        outs.append(o)
+        cache = torch.zeros(M + 100, N + 64, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, b, out=cache, row_map=rows, col_off=32)
+        outs.append(cache)
+        return outs
+
+    try:
+        ops.set_option("gemm2_bn", 256)
+        ref = run_all()
+        ops.set_option("gemm2_bn", bn)
+        got = run_all()
+    finally:
+        ops.set_option("gemm2_bn", 0)
+    assert rel_l2(ref[0], a.float() @ w.float().t() + b.float()) <= BF16_TOL
+    for x, y in zip(got, ref):
+        assert torch.equal(x, y)
+    auto = run_all()                                   # the width the host picks for this shape
+    for x, y in zip(auto, ref):
+        assert torch.equal(x, y)
+
+
 # (M, N) chosen so that the 1-CTA kernel's tile-width heuristic (gemm.cu pick_bn, 148 SMs) lands on every width it
 # can choose: 1576x3072 -> 160, 512x3072 -> 96, 1064x3072 -> 192, 1576x12288 -> 224, 716x3072 -> 128, 300x64 -> 64,
 # 100x3104 (ragged last tile) -> 64, 1900x1536 -> 96/128; K ragged too.
@@ -198,14 +239,18 @@ def test_gemm_norm_rope_epilogue_matches_oracle():
     assert rel_l2(out_pm, x2.transpose(1, 2).reshape(M2, N)) <= BF16_TOL
 
 
-@pytest.fixture(params=[0, 1], ids=["attention128", "attention64"])
+@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0)],
+                ids=["attention128-v0", "attention128-v1-earlyqk", "attention128-v2-earlyqk-3parts", "attention64"])
 def attn_kernel(request):
-    """Both attention kernels must pass every attention test: attention.cu (128-row K/V tiles, P aliased onto S) and
-    attention64.cu (64-row K/V tiles, P in its own TMEM columns, decoupled Q K^T / softmax pipeline)."""
+    """Every attention kernel / issue-order variant must pass every attention test: attention.cu (128-row K/V tiles, P
+    aliased onto S; variant 1 issues the upper half of the next Q K^T before P exists, variant 2 also publishes P in
+    64 | 32 | 32 pieces) and attention64.cu (64-row K/V tiles, P in its own TMEM columns)."""
     from regione_b200 import ops
-    ops.set_option("attn_kernel", request.param)
+    ops.set_option("attn_kernel", request.param[0])
+    ops.set_option("attn_variant", request.param[1])
     yield request.param
     ops.set_option("attn_kernel", -1)
+    ops.set_option("attn_variant", -1)
 
 
 @pytest.mark.parametrize("Sq,Skv,H", [(256, 256, 1), (128, 128, 2), (1, 130, 1), (200, 544, 2), (700, 1300, 3),
@@ -243,8 +288,9 @@ def test_attention_lazy_rescale_paths(attn_kernel):
     assert rel_l2(o, ref) <= 6e-3
 
 
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("poly", [0, 2, 3, 4])
-def test_attention_exponential_offload_variants(poly):
+def test_attention_exponential_offload_variants(poly, variant):
     """`attn_poly` of every 8 exponential pairs run as a Cody-Waite / degree-3 polynomial on the FMA pipe instead of
     MUFU.EX2 (relative error 7.5e-5, below the bf16 rounding of P): every variant stays within the same tolerance of
     the exact softmax, including rows with large late keys (lazy rescale) and a ragged KV tail (masked columns)."""
@@ -260,11 +306,13 @@ def test_attention_exponential_offload_variants(poly):
     k[Skv // 2 + 70: Skv // 2 + 90] *= 4.0                          # a second jump inside a tile
     ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
     ops.set_option("attn_poly", poly)
+    ops.set_option("attn_variant", variant)
     try:
         o = ops.attention(q, k, v, H)
         torch.cuda.synchronize()
     finally:
         ops.set_option("attn_poly", -1)
+        ops.set_option("attn_variant", -1)
     assert torch.isfinite(o.float()).all()
     assert rel_l2(o, ref) <= 6e-3
 

@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from regione_b200 import _lib, ops  # noqa: E402
 
-SHAPES = [(8704, 3072, 3072), (8704, 12288, 3072), (8704, 3072, 15360), (8704, 3072, 12288), (8192, 3072, 12288),
+SHAPES = [(8704, 3072, 3072), (8192, 3072, 3072), (4096, 3072, 15360), (8704, 12288, 3072), (8704, 3072, 15360), (8704, 3072, 12288), (8192, 3072, 12288),
           (1576, 3072, 3072), (1576, 12288, 3072), (1576, 3072, 15360), (1064, 3072, 3072), (1064, 3072, 12288),
           (512, 3072, 3072), (512, 12288, 3072)]
 
@@ -58,6 +58,12 @@ def main():
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs, rope_map=pos)
             fns["ours_norm_rope(pair-major table)"] = lambda: ops.gemm(
                 a, w, b, out=out, epilogue=_lib.EPI_NORM_ROPE, norm_w=nw, rope_cs=cs_pm, rope_map=pos, rope_ld=S)
+        if M >= 2048:                        # the CTA-pair kernel with its earlier fixed 256-wide tile
+            def fixed256():
+                ops.set_option("gemm2_bn", 256)
+                ops.gemm(a, w, b, out=out)
+                ops.set_option("gemm2_bn", 0)
+            fns["ours(256-wide tiles)"] = fixed256
         if M < 2048 and N % 256 == 0:        # the CTA-pair kernel below its default row threshold
             def pair():
                 ops.set_option("2cta_min_m", 1)
