@@ -151,10 +151,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * kMaxBN;
-      gemm_epilogue_row<EPI>(p, taddr, m_blk * BM + r, n_blk * bn, bn);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      gemm_epilogue_row<EPI>(p, taddr, m_blk * BM + r, n_blk * bn, bn, TmemRelease{&tempty_bar[acc], -1});
     }
   }
 
@@ -302,15 +299,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_group_kernel(const __grid_co
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * kMaxBN;
       const GemmDev& p = g.p[t.prob];
       const int m = t.m_blk * BM + r, n0 = t.n_blk * bn;
+      const TmemRelease rel{&tempty_bar[acc], -1};
       switch (g.epi[t.prob]) {
-        case EPI_STORE: gemm_epilogue_row<EPI_STORE>(p, taddr, m, n0, bn); break;
-        case EPI_GELU: gemm_epilogue_row<EPI_GELU>(p, taddr, m, n0, bn); break;
-        case EPI_GATE_RES: gemm_epilogue_row<EPI_GATE_RES>(p, taddr, m, n0, bn); break;
-        default: gemm_epilogue_row<EPI_NORM_ROPE>(p, taddr, m, n0, bn); break;
+        case EPI_STORE: gemm_epilogue_row<EPI_STORE>(p, taddr, m, n0, bn, rel); break;
+        case EPI_GELU: gemm_epilogue_row<EPI_GELU>(p, taddr, m, n0, bn, rel); break;
+        case EPI_GATE_RES: gemm_epilogue_row<EPI_GATE_RES>(p, taddr, m, n0, bn, rel); break;
+        default: gemm_epilogue_row<EPI_NORM_ROPE, false, 0>(p, taddr, m, n0, bn, rel); break;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -473,9 +468,14 @@ void* get_tensor_map_encoder() { return reinterpret_cast<void*>(tensor_map_encod
 cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return cudaSuccess;  // empty edited set: nothing to do
   if (!gemm_args_ok(a)) return cudaErrorInvalidValue;
-  // large-M launches (FULL steps) go to the CTA-pair kernel; RGE_2CTA_MIN_M=0 disables it
+  // Large-M launches (FULL steps) go to the CTA-pair kernel, and so do REGION-sized ones whose rows fill 256-row
+  // tiles well (<= 15 % padding: 512 + 1064 = 1576 rows -> 7 tiles; the 1-CTA kernel is bound by its L2 -> shared
+  // memory operand traffic there). RGE_2CTA_MIN_M: -1 = this rule, 0 = never, n = from n rows on.
   const int min_m_2cta = tuning().min_m_2cta;
-  if (min_m_2cta > 0 && a.M >= min_m_2cta && a.N % 256 == 0) {
+  const long padded = ((long)a.M + 255) / 256 * 256;
+  const bool pair = min_m_2cta < 0 ? (a.M >= 2048 || (a.M >= 1024 && padded * 100 <= (long)a.M * 115))
+                                   : (min_m_2cta > 0 && a.M >= min_m_2cta);
+  if (pair && a.N % 16 == 0) {
     cudaError_t e = launch_gemm_2cta(a, num_sms, stream);
     if (e != cudaErrorNotSupported) return e;
   }

@@ -142,10 +142,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      gemm_epilogue_row<EPI>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * bn, bn);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+      gemm_epilogue_row<EPI, true>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * bn, bn,
+                                   TmemRelease{&tempty_bar[acc], 0});
     }
   }
 

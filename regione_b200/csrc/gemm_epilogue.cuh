@@ -126,11 +126,115 @@ __device__ __forceinline__ void load_residual(const GemmDev& p, uint4 (&rv)[4], 
   for (int t = 0; t < 4; ++t) rv[t] = make_uint4(0, 0, 0, 0);
 }
 
+// Hands a TMEM accumulator back to the MMA issuer: every lane's tcgen05.ld of it has completed (the caller waited),
+// one lane arrives on the `tempty` barrier - of this CTA, or of the pair's leader CTA (cluster_cta >= 0).
+struct TmemRelease {
+  uint64_t* bar;
+  int cluster_cta;
+  __device__ __forceinline__ void operator()() const {
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      if (cluster_cta < 0) mbar_arrive(bar);
+      else mbar_arrive_cluster(bar, (uint32_t)cluster_cta);
+    }
+  }
+};
+
+// EPI_NORM_ROPE for NH (1 or 2) consecutive heads of this thread's row: per-head RMSNorm of the bf16-rounded
+// (acc + bias), weight, rotary embedding, store. ONE pass over TMEM: the rounded values are exactly representable in
+// bf16, so the whole head is kept as 64 packed bf16 pairs in registers while the sum of squares accumulates (the
+// 32-column TMEM loads are double-buffered), the accumulator is handed back to the MMA issuer (`release`, when this
+// is the tile's last head group) BEFORE the normalise / rotate / store pass, and that pass reads each rotary pair once
+// for both heads (the rotation depends on the row only), with the next chunk's pairs requested a chunk ahead.
+template <int NH>
+__device__ __forceinline__ void norm_rope_heads(const GemmDev& p, uint32_t taddr, __nv_bfloat16* out_ptr, int n0,
+                                                const float2* cs_base, long cs_step, bool valid,
+                                                const TmemRelease* release) {
+  uint32_t xp[NH][64];
+  float rstd[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    float ss0 = 0.f, ss1 = 0.f;
+    uint32_t va[32], vb[32];
+    tmem_ld32(taddr + h * 128, va);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld_wait();
+      uint32_t (&cur)[32] = (c & 1) ? vb : va;
+      if (c < 3) tmem_ld32(taddr + h * 128 + (c + 1) * 32, (c & 1) ? va : vb);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float b[8];
+        if (p.bias) ld_vec8(p.bias + n0 + h * 128 + c * 32 + 8 * g, b);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float x0 = __uint_as_float(cur[8 * g + j]) + (p.bias ? b[j] : 0.f);
+          const float x1 = __uint_as_float(cur[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
+          const uint32_t u = pack_bf16x2(x0, x1);
+          xp[h][c * 16 + 4 * g + (j >> 1)] = u;
+          const float r0 = __uint_as_float(u << 16), r1 = __uint_as_float(u & 0xffff0000u);
+          ss0 = fmaf(r0, r0, ss0);
+          ss1 = fmaf(r1, r1, ss1);
+        }
+      }
+    }
+    rstd[h] = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + 1e-6f);
+  }
+  if (release) (*release)();
+  float2 cs[16], cs_next[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cs[j] = valid ? __ldg(cs_base + (long)j * cs_step) : make_float2(1.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < 3) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        cs_next[j] = valid ? __ldg(cs_base + (long)((c + 1) * 16 + j) * cs_step) : make_float2(1.f, 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      uint32_t o[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float w[8];
+        ld_vec8(p.norm_w + c * 32 + 8 * g, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t u = xp[h][c * 16 + 4 * g + j];
+          float x0 = __uint_as_float(u << 16) * rstd[h], x1 = __uint_as_float(u & 0xffff0000u) * rstd[h];
+          bf16_round2(x0, x1);
+          x0 *= w[2 * j];
+          x1 *= w[2 * j + 1];
+          bf16_round2(x0, x1);
+          const float2 t = cs[4 * g + j];
+          o[4 * g + j] = pack_bf16x2(x0 * t.x - x1 * t.y, x1 * t.x + x0 * t.y);
+        }
+      }
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0 + h * 128 + c * 32);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+      }
+    }
+    if (c < 3) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cs[j] = cs_next[j];
+    }
+  }
+}
+
 // taddr: TMEM address of this thread's row (lane field set) at column 0 of the accumulator; m: global row;
 // n_base: first global column of the tile; bn: tile width (multiple of 16; of 128 for EPI_NORM_ROPE). All 32 lanes of
-// the warp must call this together.
-template <int EPI>
-__device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t taddr, int m, int n_base, int bn) {
+// the warp must call this together. kTail16: the tile width may be an odd multiple of 16 (CTA-pair kernel only - the
+// extra code path costs the grouped 1-CTA kernel, which inlines all four epilogues, its register budget).
+// `release` hands the accumulator back to the MMA issuer; it is called exactly once, as soon as the last TMEM read of
+// the tile has completed (EPI_NORM_ROPE: before the store pass).
+// kRopeHeads: heads EPI_NORM_ROPE processes together in its single-pass form (2: one rotary read for two heads, ~250
+// registers); 0 = the two-pass form with few registers for the grouped kernel, which inlines all four epilogues.
+template <int EPI, bool kTail16 = false, int kRopeHeads = 2>
+__device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t taddr, int m, int n_base, int bn,
+                                                  const TmemRelease& release) {
   const bool valid = m < p.M;
   const long out_row = valid ? (long)((p.row_map ? __ldg(p.row_map + m) : m) + p.row_off) : 0;
   __nv_bfloat16* out_ptr = p.out + out_row * p.ldo + p.col_off;
@@ -141,70 +245,90 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
     // 32 separate sectors
     const float2* cs_base = p.rope_ld > 0 ? p.rope_cs + rope_row : p.rope_cs + rope_row * 64;
     const long cs_step = p.rope_ld > 0 ? p.rope_ld : 1;
+    if constexpr (kRopeHeads == 0) {
+      // two passes over TMEM, few registers (the grouped kernel inlines all four epilogues)
 #pragma unroll 1
-    for (int h = 0; h < bn / 128; ++h) {
-      const int n0 = n_base + h * 128;
-      if (n0 >= p.N) break;
-      // pass 1: sum of squares of the bf16-rounded (acc + bias) over the head, two 32-column TMEM loads in flight
-      float ss0 = 0.f, ss1 = 0.f;
+      for (int h = 0; h < bn / 128; ++h) {
+        const int n0 = n_base + h * 128;
+        if (n0 >= p.N) break;
+        // pass 1: sum of squares of the bf16-rounded (acc + bias) over the head, two 32-column TMEM loads in flight
+        float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t v[64];
-        tmem_ld32p(taddr + h * 128 + c * 32, v);
-        tmem_ld32p(taddr + h * 128 + c * 32 + 32, v + 32);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t v[64];
+          tmem_ld32p(taddr + h * 128 + c * 32, v);
+          tmem_ld32p(taddr + h * 128 + c * 32 + 32, v + 32);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float b[8];
-          if (p.bias) ld_vec8(p.bias + n0 + c * 32 + 8 * g, b);
+          for (int g = 0; g < 8; ++g) {
+            float b[8];
+            if (p.bias) ld_vec8(p.bias + n0 + c * 32 + 8 * g, b);
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
-            float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
-            bf16_round2(x0, x1);
-            ss0 = fmaf(x0, x0, ss0);
-            ss1 = fmaf(x1, x1, ss1);
+            for (int j = 0; j < 8; j += 2) {
+              float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
+              float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
+              bf16_round2(x0, x1);
+              ss0 = fmaf(x0, x0, ss0);
+              ss1 = fmaf(x1, x1, ss1);
+            }
+          }
+        }
+        const float rstd = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + 1e-6f);
+        // pass 2: normalise, weight, rotate, store; the rotary pairs of chunk c are requested before its TMEM load
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + h * 128 + c * 32, v);
+          float2 cs[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            cs[j] = valid ? __ldg(cs_base + (long)(c * 16 + j) * cs_step) : make_float2(1.f, 0.f);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float b[8], w[8];
+            if (p.bias) ld_vec8(p.bias + n0 + c * 32 + 8 * g, b);
+            ld_vec8(p.norm_w + c * 32 + 8 * g, w);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
+              float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
+              bf16_round2(x0, x1);
+              x0 *= rstd;
+              x1 *= rstd;
+              bf16_round2(x0, x1);
+              x0 *= w[j];
+              x1 *= w[j + 1];
+              bf16_round2(x0, x1);
+              const float2 t = cs[4 * g + (j >> 1)];
+              o[4 * g + (j >> 1)] = pack_bf16x2(x0 * t.x - x1 * t.y, x1 * t.x + x0 * t.y);
+            }
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0 + c * 32);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
           }
         }
       }
-      const float rstd = rsqrtf((ss0 + ss1) * (1.0f / 128.0f) + 1e-6f);
-      // pass 2: normalise, weight, rotate, store; the rotary pairs of chunk c are requested before its TMEM load
+      release();
+    } else {
+      int heads = (p.N - n_base) / 128;
+      if (heads > bn / 128) heads = bn / 128;
+      bool released = false;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + h * 128 + c * 32, v);
-        float2 cs[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          cs[j] = valid ? __ldg(cs_base + (long)(c * 16 + j) * cs_step) : make_float2(1.f, 0.f);
-        tmem_ld_wait();
-        uint32_t o[16];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float b[8], w[8];
-          if (p.bias) ld_vec8(p.bias + n0 + c * 32 + 8 * g, b);
-          ld_vec8(p.norm_w + c * 32 + 8 * g, w);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float x0 = __uint_as_float(v[8 * g + j]) + (p.bias ? b[j] : 0.f);
-            float x1 = __uint_as_float(v[8 * g + j + 1]) + (p.bias ? b[j + 1] : 0.f);
-            bf16_round2(x0, x1);
-            x0 *= rstd;
-            x1 *= rstd;
-            bf16_round2(x0, x1);
-            x0 *= w[j];
-            x1 *= w[j + 1];
-            bf16_round2(x0, x1);
-            const float2 t = cs[4 * g + (j >> 1)];
-            o[4 * g + (j >> 1)] = pack_bf16x2(x0 * t.x - x1 * t.y, x1 * t.x + x0 * t.y);
-          }
-        }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0 + c * 32);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-        }
+      for (int h = 0; h < heads; h += kRopeHeads) {
+        const bool last = h + kRopeHeads >= heads;
+        if (kRopeHeads == 2 && h + 1 < heads)
+          norm_rope_heads<kRopeHeads>(p, taddr + h * 128, out_ptr, n_base + h * 128, cs_base, cs_step, valid,
+                             last ? &release : nullptr);
+        else
+          norm_rope_heads<1>(p, taddr + h * 128, out_ptr, n_base + h * 128, cs_base, cs_step, valid,
+                             last ? &release : nullptr);
+        released = released || last;
       }
+      if (!released) release();
     }
   } else {
     // software pipeline over 32-column chunks: the TMEM load (and, for GATE_RES, the residual-row loads, whose L2 /
@@ -212,10 +336,14 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
     int cols = p.N - n_base;
     if (cols > bn) cols = bn;
     const int n_chunks = cols / 32;
-    const bool tail16 = (cols & 16) != 0;   // tile widths are multiples of 16 (CTA-pair kernel: 240, 208, 176, ...)
+    const bool tail16 = kTail16 && (cols & 16) != 0;   // CTA-pair kernel: widths 240, 208, 176, ...
     uint32_t va[32], vb[32];
     uint4 ra[4], rb[4];
-    if (n_chunks > 0) {
+    if constexpr (!kTail16) {
+      if (n_chunks <= 0) { release(); return; }
+      tmem_ld32(taddr, va);
+      load_residual<EPI>(p, ra, m, n_base, valid);
+    } else if (n_chunks > 0) {
       tmem_ld32(taddr, va);
       load_residual<EPI>(p, ra, m, n_base, valid);
     }
@@ -236,12 +364,13 @@ __device__ __forceinline__ void gemm_epilogue_row(const GemmDev& p, uint32_t tad
         epilogue_chunk<EPI>(p, vb, rb, out_ptr, n_base + (c + 1) * 32, valid);
       }
     }
-    if (tail16) {
+    if constexpr (kTail16) if (tail16) {
       tmem_ld16p(taddr + n_chunks * 32, va);
       load_residual<EPI, 2>(p, ra, m, n_base + n_chunks * 32, valid);
       tmem_ld_wait();
       epilogue_chunk<EPI, 2>(p, va, ra, out_ptr, n_base + n_chunks * 32, valid);
     }
+    release();
   }
 }
 

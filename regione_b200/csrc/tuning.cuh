@@ -18,11 +18,10 @@ inline int current_device() {
 
 struct Tuning {
   int attn_poly;     // RGE_ATTN_POLY:   exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
-  int attn_variant;  // RGE_ATTN_VARIANT: MMA issue order / P granularity of attention.cu (0, 1, 2), -1 = default
   int attn_kernel;   // RGE_ATTN_KERNEL: 0 = attention.cu, 1 = attention64.cu (decoupled pipeline), -1 = default
   int gemm_bn;       // RGE_GEMM_BN:     forced tile width of the 1-CTA GEMM, 0 = choose per launch
   int gemm2_bn;      // RGE_GEMM2_BN:    forced tile width of the CTA-pair GEMM (multiple of 16), 0 = choose per launch
-  int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never
+  int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never, -1 = per-shape rule (default)
   int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
   int trim_last;     // RGE_TRIM_LAST:   1 = the last block computes only the rows whose output is kept (default)
   int nvtx;          // RGE_NVTX:        1 = NVTX ranges per step / block / stage (profilers only)
@@ -37,11 +36,10 @@ inline Tuning& tuning() {
   static Tuning t = [] {
     Tuning x;
     x.attn_poly = env_int("RGE_ATTN_POLY", -1);
-    x.attn_variant = env_int("RGE_ATTN_VARIANT", -1);
     x.attn_kernel = env_int("RGE_ATTN_KERNEL", -1);
     x.gemm_bn = env_int("RGE_GEMM_BN", 0);
     x.gemm2_bn = env_int("RGE_GEMM2_BN", 0);
-    x.min_m_2cta = env_int("RGE_2CTA_MIN_M", 2048);
+    x.min_m_2cta = env_int("RGE_2CTA_MIN_M", -1);
     const char* r = getenv("RGE_RASTER");
     x.raster = !r ? -1 : (r[0] == 'n' ? 1 : (r[0] == 'm' ? 0 : -1));
     x.trim_last = env_int("RGE_TRIM_LAST", 1);
@@ -55,7 +53,6 @@ inline Tuning& tuning() {
 inline bool set_tuning(const char* name, int value) {
   Tuning& t = tuning();
   if (!strcmp(name, "attn_poly")) t.attn_poly = value;
-  else if (!strcmp(name, "attn_variant")) t.attn_variant = value;
   else if (!strcmp(name, "attn_kernel")) t.attn_kernel = value;
   else if (!strcmp(name, "gemm_bn")) t.gemm_bn = value;
   else if (!strcmp(name, "gemm2_bn")) t.gemm2_bn = value;

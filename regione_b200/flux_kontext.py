@@ -254,7 +254,7 @@ class RegionEFluxKontextPipelineMixin:
             negative_prompt_embeds is not None and negative_pooled_prompt_embeds is not None)
         do_true_cfg = true_cfg_scale > 1 and has_neg_prompt                                                 # :180
         for k in ("ip_adapter_image", "ip_adapter_image_embeds", "negative_ip_adapter_image",
-                  "negative_ip_adapter_image_embeds", "callback_on_step_end", "sigmas"):
+                  "negative_ip_adapter_image_embeds", "sigmas"):
             if unused.get(k) is not None:
                 raise NotImplementedError(f"regione_b200: `{k}` is outside the hot path and not supported")
         known = {"negative_prompt", "negative_prompt_2", "negative_prompt_embeds", "negative_pooled_prompt_embeds",
@@ -322,7 +322,10 @@ class RegionEFluxKontextPipelineMixin:
         self.scheduler._step_index = 0
         negative = (negative_prompt_embeds, negative_pooled_prompt_embeds, float(true_cfg_scale)) if do_true_cfg else None
         latents = self.regione_denoise(latents, image_latents, latent_ids, text_ids, prompt_embeds,
-                                       pooled_prompt_embeds, guidance_scale, height, width, negative=negative)
+                                       pooled_prompt_embeds, guidance_scale, height, width, negative=negative,
+                                       callback_on_step_end=unused.get("callback_on_step_end"),
+                                       callback_on_step_end_tensor_inputs=unused.get(
+                                           "callback_on_step_end_tensor_inputs") or ["latents"])
         if output_type == "latent":
             image = latents
         else:
@@ -334,9 +337,12 @@ class RegionEFluxKontextPipelineMixin:
         return types.SimpleNamespace(images=image)
 
     def regione_denoise(self, latents, image_latents, latent_ids, text_ids, prompt_embeds, pooled_prompt_embeds,
-                        guidance_scale, height, width, negative=None):
+                        guidance_scale, height, width, negative=None, callback_on_step_end=None,
+                        callback_on_step_end_tensor_inputs=("latents",)):
         """The hot loop, inplace.py:287-392. `negative` = (negative_prompt_embeds, negative_pooled_prompt_embeds,
-        true_cfg_scale) enables the second forward of true-CFG (:349-364)."""
+        true_cfg_scale) enables the second forward of true-CFG (:349-364). `callback_on_step_end(pipe, i, t, kwargs)`
+        runs after every scheduler step and may replace `latents` (:377-385); `self._interrupt` skips the rest of a
+        computed step exactly as the reference's `continue` does (:321-322)."""
         M = MANAGER
         N = M.inference_step
         sch = self.scheduler
@@ -373,6 +379,8 @@ class RegionEFluxKontextPipelineMixin:
                 x = sch.step(cache, t, x, return_dict=False, reuse_ratio=ratio)[0]
                 self.regione_trace["modes"].append("SKIP")
             else:
+                if getattr(self, "_interrupt", False):                                            # :321-322
+                    continue
                 cur = M.current_step
                 full = cur <= M.warmup_step - 1 or cur > N - M.post_step - 1 or cur == M.prev_refresh_step   # :331
                 timestep = t.expand(1).to(x.dtype)                                                # :334
@@ -392,6 +400,22 @@ class RegionEFluxKontextPipelineMixin:
                 cache = noise_pred                                                                # :365
                 x = sch.step(noise_pred, t, x, return_dict=False)[0]                               # :369
                 self.regione_trace["modes"].append("FULL" if full else "REGION")
+            if callback_on_step_end is not None:                                                  # :377-385
+                kw = {}
+                for name in callback_on_step_end_tensor_inputs:
+                    if name == "latents":
+                        kw[name] = x[None]
+                    elif name == "prompt_embeds":
+                        kw[name] = prompt_embeds
+                    else:
+                        raise KeyError(f"regione_b200: callback tensor input `{name}` is not available on this path")
+                out = callback_on_step_end(self, i, ts_host[i], kw) or {}
+                new_x = out.pop("latents", None)
+                if new_x is not None and new_x is not kw.get("latents"):
+                    x = new_x[0].contiguous()
+                if out.get("prompt_embeds", prompt_embeds) is not prompt_embeds:
+                    raise NotImplementedError("regione_b200: the prompt embeddings are registered once per image; "
+                                              "a callback cannot replace them mid-loop")
             x, latent_ids = M.step(x, latent_ids)                                                 # :392
             if record:
                 self.regione_trace["latents"].append(x.clone())

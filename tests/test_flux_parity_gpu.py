@@ -141,3 +141,46 @@ def test_launch_schedule_variants_give_the_same_image(env, monkeypatch):
         monkeypatch.setenv(k, v)
     _check(*_run_both(syn.TINY, (16, 16), 32, 0.25, DEFAULT))
     _check(*_run_both(syn.TINY, (12, 20), 40, 0.0, DEFAULT, seed=5))      # empty edited set through the grouped path
+
+
+def test_callback_on_step_end_and_interrupt():
+    """inplace.py:377-385 / :321-322: the callback sees every step's latents at the step's own token count, may
+    replace them, and an identity callback leaves the image bit-identical; `interrupt` skips a computed step exactly
+    like the reference's `continue` (which then trips the reference's own step-counter assertion)."""
+    from regione_b200 import RegionEHelper
+    from standins import synthetic as syn
+    pipe = syn.build_pipeline(syn.TINY, seed=110, device="cuda")
+    helper = RegionEHelper(pipe)
+    helper.set_params(**DEFAULT)
+    helper.enable()
+    pipe = helper.pipeline
+    inp = syn.make_inputs(7, 16, 16, 32, syn.TINY["ctx_dim"], syn.TINY["pooled_dim"], rho=0.25, device="cuda")
+    kw = {k: v for k, v in inp.items() if k != "intended_mask"}
+    call = dict(guidance_scale=2.5, num_inference_steps=28, output_type="latent", return_dict=False, **kw)
+    base = pipe(**call)[0]
+    seen = []
+
+    def identity(p, i, t, tensors):
+        seen.append((i, float(t), tuple(tensors["latents"].shape)))
+        return {}
+
+    same = pipe(callback_on_step_end=identity, **call)[0]
+    assert torch.equal(same, base)
+    assert [s[0] for s in seen] == list(range(28))
+    n_e = pipe.regione_trace["edited_ids"].numel()
+    assert seen[0][2] == (1, 256, 64) and seen[10][2] == (1, n_e, 64) and seen[-1][2] == (1, 256, 64)
+
+    def halve_at_3(p, i, t, tensors):
+        return {"latents": tensors["latents"] * 0.5} if i == 3 else {}
+
+    changed = pipe(callback_on_step_end=halve_at_3, **call)[0]
+    assert not torch.equal(changed, base) and torch.isfinite(changed.float()).all()
+
+    def stop_at_5(p, i, t, tensors):
+        if i == 5:
+            p._interrupt = True
+        return {}
+
+    with pytest.raises(AssertionError):       # the reference's `continue` skips MANAGER.step: its :293 assert fires
+        pipe(callback_on_step_end=stop_at_5, **call)
+    helper.disable()

@@ -40,10 +40,11 @@ def test_gemm_store_matches_linear(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(2048, 256, 64), (2049, 512, 192), (4000, 3072, 256), (2304, 768, 3072),
-                                   (4100, 512, 12288)])   # last: A > 96 MB -> tiles walk along N (pick_n_fast)
+                                   (4100, 512, 12288),    # A > 96 MB -> tiles walk along N (pick_n_fast)
+                                   (1576, 3072, 192), (1200, 1536, 320)])   # REGION-sized rows that fill 256-row tiles
 def test_gemm_cta_pair_kernel_all_epilogues(M, N, K):
-    """M >= 2048 and N % 256 == 0 dispatch to the cta_group::2 kernel (gemm2.cu): ragged M (second CTA partly or
-    fully out of range), every epilogue, scatter."""
+    """M >= 2048, and REGION-sized M with <= 15 % padding to 256-row tiles, dispatch to the cta_group::2 kernel
+    (gemm2.cu): ragged M (second CTA partly or fully out of range), every epilogue, scatter."""
     from regione_b200 import _lib, ops
     g = _gen(21)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -116,12 +117,21 @@ def test_gemm_cta_pair_kernel_tile_widths_bit_identical(bn):
         assert torch.equal(x, y)
 
 
+@pytest.fixture
+def one_cta_kernel():
+    """Keeps every launch on the 1-CTA kernel (the per-shape rule would send well-filled REGION sizes to the CTA pair)."""
+    from regione_b200 import ops
+    ops.set_option("2cta_min_m", 0)
+    yield
+    ops.set_option("2cta_min_m", -1)
+
+
 # (M, N) chosen so that the 1-CTA kernel's tile-width heuristic (gemm.cu pick_bn, 148 SMs) lands on every width it
 # can choose: 1576x3072 -> 160, 512x3072 -> 96, 1064x3072 -> 192, 1576x12288 -> 224, 716x3072 -> 128, 300x64 -> 64,
 # 100x3104 (ragged last tile) -> 64, 1900x1536 -> 96/128; K ragged too.
 @pytest.mark.parametrize("M,N,K", [(1576, 3072, 320), (512, 3072, 256), (1064, 3072, 192), (1576, 12288, 128),
                                    (716, 3072, 456), (300, 64, 3072), (100, 3104, 64), (1900, 1536, 200)])
-def test_gemm_region_step_tile_widths_all_epilogues(M, N, K):
+def test_gemm_region_step_tile_widths_all_epilogues(M, N, K, one_cta_kernel):
     from regione_b200 import _lib, ops
     g = _gen(31)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -239,18 +249,14 @@ def test_gemm_norm_rope_epilogue_matches_oracle():
     assert rel_l2(out_pm, x2.transpose(1, 2).reshape(M2, N)) <= BF16_TOL
 
 
-@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0)],
-                ids=["attention128-v0", "attention128-v1-earlyqk", "attention128-v2-earlyqk-3parts", "attention64"])
+@pytest.fixture(params=[0, 1], ids=["attention128", "attention64"])
 def attn_kernel(request):
-    """Every attention kernel / issue-order variant must pass every attention test: attention.cu (128-row K/V tiles, P
-    aliased onto S; variant 1 issues the upper half of the next Q K^T before P exists, variant 2 also publishes P in
-    64 | 32 | 32 pieces) and attention64.cu (64-row K/V tiles, P in its own TMEM columns)."""
+    """Both attention kernels must pass every attention test: attention.cu (128-row K/V tiles, P aliased onto S) and
+    attention64.cu (64-row K/V tiles, P in its own TMEM columns, decoupled Q K^T / softmax pipeline)."""
     from regione_b200 import ops
-    ops.set_option("attn_kernel", request.param[0])
-    ops.set_option("attn_variant", request.param[1])
+    ops.set_option("attn_kernel", request.param)
     yield request.param
     ops.set_option("attn_kernel", -1)
-    ops.set_option("attn_variant", -1)
 
 
 @pytest.mark.parametrize("Sq,Skv,H", [(256, 256, 1), (128, 128, 2), (1, 130, 1), (200, 544, 2), (700, 1300, 3),
@@ -288,9 +294,8 @@ def test_attention_lazy_rescale_paths(attn_kernel):
     assert rel_l2(o, ref) <= 6e-3
 
 
-@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("poly", [0, 2, 3, 4])
-def test_attention_exponential_offload_variants(poly, variant):
+def test_attention_exponential_offload_variants(poly):
     """`attn_poly` of every 8 exponential pairs run as a Cody-Waite / degree-3 polynomial on the FMA pipe instead of
     MUFU.EX2 (relative error 7.5e-5, below the bf16 rounding of P): every variant stays within the same tolerance of
     the exact softmax, including rows with large late keys (lazy rescale) and a ragged KV tail (masked columns)."""
@@ -306,13 +311,11 @@ def test_attention_exponential_offload_variants(poly, variant):
     k[Skv // 2 + 70: Skv // 2 + 90] *= 4.0                          # a second jump inside a tile
     ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
     ops.set_option("attn_poly", poly)
-    ops.set_option("attn_variant", variant)
     try:
         o = ops.attention(q, k, v, H)
         torch.cuda.synchronize()
     finally:
         ops.set_option("attn_poly", -1)
-        ops.set_option("attn_variant", -1)
     assert torch.isfinite(o.float()).all()
     assert rel_l2(o, ref) <= 6e-3
 

@@ -1,6 +1,6 @@
 """Isolated attention throughput (sustained ~1.2 s per entry, back to back under the power cap) at the FULL and REGION
-shapes of the hot path: this library's kernel for every issue-order variant (attn_variant) and exponential-offload variant
-(attn_poly = 0 / 2 / 3 of 8 pairs on the FMA pipe) next to the reference's own attention call `flash_attn_func` (inplace.py:796-801; flash-attn 2.8,
+shapes of the hot path: this library's kernel for every exponential-offload variant (attn_poly = 0 / 2 / 3 / 4 of 8
+pairs on the FMA pipe) next to the reference's own attention call `flash_attn_func` (inplace.py:796-801; flash-attn 2.8,
 FA2 kernels compiled for sm_100) and cuDNN's fused SDPA through torch. Usage: python tools/attn_bench.py [--quick]"""
 import os
 import sys
@@ -41,13 +41,10 @@ def main():
         o = torch.empty_like(q)
         fl = 4.0 * Sq * Skv * 128 * H
         res = {}
-        for var in (0, 1, 2):
-            for poly in (0, 2, 3):
-                ops.set_option("attn_variant", var)
-                ops.set_option("attn_poly", poly)
-                res[f"ours v{var} poly={poly}"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
+        for poly in (0, 2, 3, 4):
+            ops.set_option("attn_poly", poly)
+            res[f"ours poly={poly}"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         ops.set_option("attn_poly", -1)
-        ops.set_option("attn_variant", -1)
         ops.set_option("attn_kernel", 1)
         res["ours kernel=attention64"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         ops.set_option("attn_kernel", -1)

@@ -64,12 +64,18 @@ def main():
                 ops.gemm(a, w, b, out=out)
                 ops.set_option("gemm2_bn", 0)
             fns["ours(256-wide tiles)"] = fixed256
-        if M < 2048 and N % 256 == 0:        # the CTA-pair kernel below its default row threshold
+        if M < 2048 and N % 256 == 0:        # both kernels where the per-shape rule decides between them
             def pair():
                 ops.set_option("2cta_min_m", 1)
                 ops.gemm(a, w, b, out=out)
-                ops.set_option("2cta_min_m", 2048)
+                ops.set_option("2cta_min_m", -1)
             fns["ours(cta-pair kernel)"] = pair
+
+            def single():
+                ops.set_option("2cta_min_m", 0)
+                ops.gemm(a, w, b, out=out)
+                ops.set_option("2cta_min_m", -1)
+            fns["ours(1-cta kernel)"] = single
         res = {}
         for name, fn in fns.items():
             for _ in range(3):
