@@ -357,6 +357,12 @@ struct rge_handle {
   cudaStream_t sattn = nullptr;
   cudaEvent_t ev_attn = nullptr, ev_q = nullptr;
   bool fill_attn_tail = true;
+  // The adaLN modulation vectors of all blocks are one HBM-bound batched GEMV over 6.5 GB of weights (~0.9 ms) that
+  // only depends on the time embedding. The vectors of the first kModHeadBlocks blocks are computed on the caller's
+  // stream; the rest runs on this side stream beside those blocks' tensor-bound GEMMs (its CTAs fit next to a GEMM
+  // CTA: 16 KB of shared memory) and is joined before the first block that reads it.
+  cudaStream_t smod = nullptr;
+  cudaEvent_t ev_temb = nullptr, ev_mod = nullptr;
   // RGE_GROUPED=1: steps whose GEMMs all take the 1-CTA path (REGION steps: few rows) launch the independent GEMMs of
   // a stage as ONE grouped persistent kernel on the caller's stream instead of fanning them out over the side
   // streams. Off by default: measured 43.5 ms vs 41.5 ms per REGION step (profiles/r01_step_times_grouped*.log) -
@@ -442,6 +448,7 @@ struct StepRun {
   bf16 *x_img, *n_img_p, *big_img;
   int idle_sms;             // SMs the last (partial) wave of the attention grid leaves idle
   bool fill_tail;           // ... and whether the single blocks' MLP-up GEMM runs there beside attention
+  int tail_cols;            // ... or, when the whole GEMM does not fit there, how many of its output columns do
 
   StepRun(rge_handle* h_, cudaStream_t st_, int pass_, int T_, int M_)
       : h(h_), st(st_), pass(pass_), D(h_->D), Dm(h_->Dm), T(T_), S(T_ + h_->L + h_->C), M(M_), MA(T_ + M_) {
@@ -460,8 +467,17 @@ struct StepRun {
     const int n_attn_ctas = ((MA + 255) / 256) * h->H;
     const int attn_tail = n_attn_ctas % h->num_sms;
     idle_sms = attn_tail ? h->num_sms - attn_tail : 0;
-    fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 &&
-                2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * 4.0 * 256.0 * S * 128.0;
+    const double attn_cta_flop = 4.0 * 256.0 * S * 128.0;
+    fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 && 2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * attn_cta_flop;
+    // FULL steps: 816 attention CTAs = 5.51 waves; the 72 SMs the last wave leaves idle take as many 256-column
+    // blocks of the MLP-up GEMM as fit into one attention-CTA time (the rest of the GEMM runs before attention)
+    tail_cols = 0;
+    if (fan && h->fill_attn_tail && !fill_tail && idle_sms >= 16) {
+      const double per_col = 2.0 * MA * (double)D;
+      long cols = (long)(0.9 * idle_sms * attn_cta_flop / per_col) / 256 * 256;
+      if (cols > Dm - 256) cols = (Dm - 256) / 256 * 256;
+      tail_cols = cols >= 256 && Dm % 256 == 0 ? (int)cols : 0;
+    }
   }
 
   // makes `to` wait for everything enqueued on `from` so far
@@ -633,7 +649,7 @@ struct StepRun {
 
   // attention on the high-priority stream and the MLP-up GEMM, capped to the SMs the last attention wave leaves idle,
   // both start once `ev_q` (and, in the fan-out, the K / V events already recorded) are reached
-  int attention_beside_mlp(int b, bf16* kc, bf16* vc, bool wait_kv) const {
+  int attention_beside_mlp(const GemmArgs& mlp, bf16* kc, bf16* vc, bool wait_kv) const {
     RGE_CUDA(cudaEventRecord(h->ev_q, st));
     for (cudaStream_t s2 : {h->sattn, sT}) {
       RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_q, 0));
@@ -643,9 +659,18 @@ struct StepRun {
       }
     }
     RGE_TRY(attention(kc, vc, h->sattn));
-    RGE_TRY(one(sT, s_mlp(b), idle_sms));
+    RGE_TRY(one(sT, mlp, idle_sms));
     RGE_CUDA(link(h->sattn, h->ev_attn, st));
     return RGE_OK;
+  }
+  // columns [c0, c0 + n) of the single block's MLP-up GEMM
+  GemmArgs s_mlp_cols(int b, int c0, int n) const {
+    GemmArgs a = s_mlp(b);
+    a.W = a.W + (size_t)c0 * a.ldw;
+    if (a.bias) a.bias += c0;
+    a.col_off += c0;
+    a.N = n;
+    return a;
   }
 
   // adaLN vectors of a single block at mod: shift, scale, gate
@@ -662,7 +687,7 @@ struct StepRun {
       const GemmArgs qkv[3] = {s_q(b), s_k(b, kc), s_v(b, vc)};
       RGE_TRY(gemm_group(h, st, qkv, 3));
       if (!fill_tail) RGE_TRY(attention(kc, vc, st));
-      else RGE_TRY(attention_beside_mlp(b, kc, vc, false));
+      else RGE_TRY(attention_beside_mlp(s_mlp(b), kc, vc, false));
       RGE_CUDA(link(sT, h->ev_aux[0], st));
       return one(st, s_out(b, mod + 2 * D));
     }
@@ -672,7 +697,7 @@ struct StepRun {
     RGE_TRY(one(st, s_q(b)));
     RGE_TRY(one(sK, s_k(b, kc)));
     RGE_TRY(one(sV, s_v(b, vc)));
-    if (!fill_tail) {
+    if (!fill_tail && tail_cols == 0) {
       // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT when attention
       // starts: its CTAs and the attention CTAs share the SMs, which fills the partial last wave of either kernel
       RGE_TRY(one(sT, s_mlp(b)));
@@ -680,9 +705,11 @@ struct StepRun {
       RGE_CUDA(link(sV, h->ev_aux[2], st));
       RGE_TRY(attention(kc, vc, st));
     } else {
+      // whole GEMM beside attention (REGION steps), or its first columns before and its last `tail_cols` beside it
+      if (!fill_tail) RGE_TRY(one(sT, s_mlp_cols(b, 0, Dm - tail_cols)));
       RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
       RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
-      RGE_TRY(attention_beside_mlp(b, kc, vc, true));
+      RGE_TRY(attention_beside_mlp(fill_tail ? s_mlp(b) : s_mlp_cols(b, Dm - tail_cols, tail_cols), kc, vc, true));
     }
     RGE_CUDA(link(sT, h->ev_aux[0], st));
     return one(st, s_out(b, mod + 2 * D));
@@ -761,7 +788,7 @@ struct StepRun {
       RGE_TRY(attention(kc, vc, st));
     } else {
       RGE_TRY(gemm_group(h, st, proj, 3));
-      RGE_TRY(attention_beside_mlp(b, kc, vc, false));
+      RGE_TRY(attention_beside_mlp(s_mlp(b), kc, vc, false));
       RGE_CUDA(link(sT, h->ev_aux[0], st));
     }
     return one(st, s_out(b, mod + 2 * D));
@@ -831,6 +858,9 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
     A(cudaEventCreateWithFlags(&h->ev_attn, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
   }
+  A(cudaStreamCreateWithFlags(&h->smod, cudaStreamNonBlocking));
+  A(cudaEventCreateWithFlags(&h->ev_temb, cudaEventDisableTiming));
+  A(cudaEventCreateWithFlags(&h->ev_mod, cudaEventDisableTiming));
   if (const char* env = getenv("RGE_NO_FANOUT")) h->fanout = env[0] == '0' || env[0] == 0;
   if (const char* env = getenv("RGE_FILL_ATTN_TAIL")) h->fill_attn_tail = env[0] != '0';
   if (const char* env = getenv("RGE_GROUPED")) h->grouped = env[0] != '0';
@@ -859,6 +889,9 @@ int rge_destroy(rge_handle* h) {
   }
   if (h->ev_txt) cudaEventDestroy(h->ev_txt);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->smod) cudaStreamDestroy(h->smod);
+  if (h->ev_temb) cudaEventDestroy(h->ev_temb);
+  if (h->ev_mod) cudaEventDestroy(h->ev_mod);
   if (h->sattn) cudaStreamDestroy(h->sattn);
   if (h->ev_attn) cudaEventDestroy(h->ev_attn);
   if (h->ev_q) cudaEventDestroy(h->ev_q);
@@ -1025,8 +1058,22 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
     else if (h->cfg.guidance_embeds) RGE_LAUNCH(launch_add3(t2, gemb, nullptr, temb, D, st));
     else RGE_CUDA(cudaMemcpyAsync(temb, t2, (size_t)D * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
   }
-  // ---- adaLN modulation vectors of all blocks
-  RGE_LAUNCH(launch_gemv_batch(h->jobs + 2, h->n_mod, 6 * D, st));
+  // ---- adaLN modulation vectors: the first blocks' on `st`, the rest on the side stream (joined in the block loop)
+  constexpr int kModHeadBlocks = 2;
+  const int n_blocks = h->cfg.n_double + h->cfg.n_single;
+  int head_jobs = h->n_mod, head_blocks = n_blocks;   // default: everything on `st`
+  if (h->fanout && tuning().split_mod && n_blocks > kModHeadBlocks + 1) {
+    head_blocks = kModHeadBlocks;
+    const int hd = h->cfg.n_double < head_blocks ? h->cfg.n_double : head_blocks;
+    head_jobs = 2 * hd + (head_blocks - hd);           // two jobs per double block, one per single block
+  }
+  RGE_LAUNCH(launch_gemv_batch(h->jobs + 2, head_jobs, 6 * D, st));
+  if (head_jobs < h->n_mod) {
+    RGE_CUDA(cudaEventRecord(h->ev_temb, st));
+    RGE_CUDA(cudaStreamWaitEvent(h->smod, h->ev_temb, 0));
+    RGE_LAUNCH(launch_gemv_batch(h->jobs + 2 + head_jobs, h->n_mod - head_jobs, 6 * D, h->smod));
+    RGE_CUDA(cudaEventRecord(h->ev_mod, h->smod));
+  }
   // ---- token embedding: text rows [0,T) come from the per-image context embedding, image rows from x_embedder
   if (T > 0)
     RGE_CUDA(cudaMemcpyAsync(h->h, ext_ctx ? (const bf16*)ext_ctx : h->ctx + (size_t)pass * h->T * D,
@@ -1050,15 +1097,19 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   const bool trim = tuning().trim_last && h->fanout && !grouped && n_out < MA;
   const int last_double = trim && h->cfg.n_single == 0 ? h->cfg.n_double - 1 : -1;
   const int last_single = trim ? h->cfg.n_single - 1 : -1;
-  for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D)
+  for (int b = 0; b < h->cfg.n_double; ++b, ++layer, mod += 12 * D) {
+    if (layer == head_blocks) RGE_CUDA(cudaStreamWaitEvent(st, h->ev_mod, 0));
     RGE_TRY(b == last_double ? r.double_block_last(b, layer, mod, n_out)
             : grouped        ? r.double_block_grouped(b, layer, mod)
                              : r.double_block_fanout(b, layer, mod));
+  }
   if (!grouped && h->cfg.n_double > 0) RGE_CUDA(r.link(r.sT, h->ev_aux[0], st));
-  for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D)
+  for (int b = 0; b < h->cfg.n_single; ++b, ++layer, mod += 3 * D) {
+    if (layer == head_blocks) RGE_CUDA(cudaStreamWaitEvent(st, h->ev_mod, 0));
     RGE_TRY(b == last_single ? r.single_block_last(b, layer, mod, n_out)
             : grouped        ? r.single_block_grouped(b, layer, mod)
                              : r.single_block_fanout(b, layer, mod));
+  }
   bf16* x_img = r.x_img;
   bf16* n_img_p = r.n_img_p;
   // ---- norm_out (scale first, then shift) + proj_out on the noise rows only (App. C-9)

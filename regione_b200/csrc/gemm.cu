@@ -468,12 +468,13 @@ void* get_tensor_map_encoder() { return reinterpret_cast<void*>(tensor_map_encod
 cudaError_t launch_gemm(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return cudaSuccess;  // empty edited set: nothing to do
   if (!gemm_args_ok(a)) return cudaErrorInvalidValue;
-  // Large-M launches (FULL steps) go to the CTA-pair kernel, and so do REGION-sized ones whose rows fill 256-row
-  // tiles well (<= 15 % padding: 512 + 1064 = 1576 rows -> 7 tiles; the 1-CTA kernel is bound by its L2 -> shared
-  // memory operand traffic there). RGE_2CTA_MIN_M: -1 = this rule, 0 = never, n = from n rows on.
+  // Large-M launches (FULL steps) go to the CTA-pair kernel, and so do smaller ones whose rows fill 256-row tiles well
+  // (<= 18 % padding: 512, 872, 1576 rows; not 1064 -> 1280): the 1-CTA kernel is bound by its L2 -> shared memory
+  // operand traffic, which the pair halves (profiles/r02_gemm2_width_sweep.log: 1576 x 3072 x 3072 907 vs 805 TFLOP/s,
+  // 512 x 12288 x 3072 935 vs 877). RGE_2CTA_MIN_M: -1 = this rule, 0 = never, n = from n rows on.
   const int min_m_2cta = tuning().min_m_2cta;
   const long padded = ((long)a.M + 255) / 256 * 256;
-  const bool pair = min_m_2cta < 0 ? (a.M >= 2048 || (a.M >= 1024 && padded * 100 <= (long)a.M * 115))
+  const bool pair = min_m_2cta < 0 ? (a.M >= 2048 || padded * 100 <= (long)a.M * 118)
                                    : (min_m_2cta > 0 && a.M >= min_m_2cta);
   if (pair && a.N % 16 == 0) {
     cudaError_t e = launch_gemm_2cta(a, num_sms, stream);

@@ -7,7 +7,7 @@
 // The tile width is a launch parameter (any multiple of 16): with 74 pairs, 256-wide tiles leave the last wave of the
 // hot shapes half empty (8704 x 3072: 408 tiles = 5.51 waves, 8192 x 3072: 384 tiles = 5.19 waves - and measured
 // throughput is exactly the tail-free rate x waves / ceil(waves)); the host picks the width that minimises
-// ceil(waves) x width (pick_bn2: 240 resp. 192 for those two shapes). A narrower tile changes neither the k-order of
+// ceil(waves) x (width + per-tile overhead) (pick_bn2: 192 for the second shape). A narrower tile changes neither the k-order of
 // any output element's sum nor its epilogue, so results stay bit-identical.
 //
 //   warp 0      TMA producer (both CTAs; transaction bytes are credited to the leader's `full` barrier)
@@ -152,19 +152,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
-// Tile width: minimise  ceil(tiles / pairs) x (bn + 4)  over the multiples of 16 (of 128 for EPI_NORM_ROPE, whose
-// epilogue owns whole heads); the small constant stands for the per-tile pipeline drain and breaks ties towards the
-// wider tile. RGE_GEMM2_BN / "gemm2_bn" forces a width (256 = the fixed tile of the earlier kernel).
+// Tile width: minimise  ceil(tiles / pairs) x (bn + 60) [x 1.04 for odd multiples of 16]  over the multiples of 16 (of
+// 128 for EPI_NORM_ROPE, whose epilogue owns whole heads). The constants are fitted to the measured width sweep
+// (profiles/r02_gemm2_width_sweep.log, tools/gemm2_width_sweep.py): a narrower tile re-reads the same 128 x 64 A block
+// from shared memory for fewer FLOPs (the 256-wide tile sits exactly at the 128 B/clk the SS MMA may read), and widths
+// that are not multiples of 32 pay the 16-column epilogue tail. RGE_GEMM2_BN / "gemm2_bn" forces a width.
 int pick_bn2(const GemmArgs& a, int pairs) {
   const bool heads = a.epilogue == EPI_NORM_ROPE;
   const int forced = tuning().gemm2_bn;
   if (forced >= 16 && forced <= BN && forced % (heads ? 128 : 16) == 0) return forced;
   const long num_m = (a.M + 2 * BM - 1) / (2 * BM);
   int best = BN;
-  long best_cost = 0;
-  for (int bn = BN; bn >= 128; bn -= heads ? 128 : 16) {
+  double best_cost = 0;
+  for (int bn = BN; bn >= (heads ? 128 : 64); bn -= heads ? 128 : 16) {
     const long tiles = num_m * ((a.N + bn - 1) / bn);
-    const long cost = ((tiles + pairs - 1) / pairs) * (bn + 4);
+    const double cost = (double)((tiles + pairs - 1) / pairs) * (bn + 60) * (bn % 32 ? 1.04 : 1.0);
     if (bn == BN || cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
