@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RGE_ABI_VERSION 4
+#define RGE_ABI_VERSION 5
 
 enum rge_status {
   RGE_OK = 0,
@@ -33,7 +33,7 @@ enum rge_status {
 int rge_abi_version(void);
 const char* rge_last_error(void);
 /* Run-time tuning knob of the kernels (same names as the RGE_* environment variables they start from, lower case
- * without the prefix: "attn_kernel", "attn_poly", "gemm_bn", "gemm2_bn", "2cta_min_m", "raster", "trim_last", "nvtx"). For
+ * without the prefix: "attn_kernel", "attn_poly", "attn_split", "gemm_bn", "gemm2_bn", "2cta_min_m", "raster", "trim_last", "nvtx"). For
  * benchmarks that sweep variants inside one process; results never depend on them beyond the stated tolerances. */
 int rge_set_option(const char* name, int32_t value);
 
@@ -82,8 +82,14 @@ typedef struct rge_attn_desc {
   void* O; int64_t ldo;
   int32_t Sq, Skv, H;
   float scale;
+  /* Optional device scratch of rge_attention_workspace_bytes(H) bytes (may be NULL / 0). With it, when the full
+   * 256-row query tiles of all heads fit into one wave of CTAs and the ragged last tile alone would cost a second one
+   * (REGION steps: 512 + ~1064 rows x 24 heads), that tile is cut along K/V and merged by a small second kernel. Must
+   * not be shared between attention launches that may run concurrently. */
+  void* workspace; int64_t workspace_bytes;
 } rge_attn_desc;
 int rge_op_attention(const rge_attn_desc* d, void* stream);
+int64_t rge_attention_workspace_bytes(int32_t H);
 
 /* out = LayerNorm(x, eps 1e-6, no affine) * (1 + scale) + shift  (diffusers AdaLayerNormZero*). */
 int rge_op_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, void* out, int64_t ldo,

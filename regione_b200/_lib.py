@@ -16,7 +16,7 @@ c_void_p, c_int32, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_floa
 RGE_OK = 0
 EPI_STORE, EPI_GELU, EPI_GATE_RES, EPI_NORM_ROPE = 0, 1, 2, 3
 GEMM_FP16_ROUNDTRIP = 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 BLK_GLOBAL, BLK_DOUBLE, BLK_SINGLE = 0, 1, 2
 
 GLOBAL_SLOTS = [
@@ -70,6 +70,7 @@ class AttnDesc(C.Structure):
         ("O", c_void_p), ("ldo", c_int64),
         ("Sq", c_int32), ("Skv", c_int32), ("H", c_int32),
         ("scale", c_float),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
     ]
 
 
@@ -91,6 +92,7 @@ PROTOTYPES = {
     "rge_op_gemm": (c_int32, [C.POINTER(GemmDesc), c_void_p]),
     "rge_op_gemm_group": (c_int32, [C.POINTER(GemmDesc), c_int32, c_void_p]),
     "rge_op_attention": (c_int32, [C.POINTER(AttnDesc), c_void_p]),
+    "rge_attention_workspace_bytes": (c_int64, [c_int32]),
     "rge_op_ln_modulate": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                      c_void_p]),
     "rge_op_rmsnorm": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),

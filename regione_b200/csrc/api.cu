@@ -220,9 +220,13 @@ int rge_op_attention(const rge_attn_desc* d, void* stream) {
   a.O = (bf16*)d->O; a.ldo = d->ldo;
   a.Sq = d->Sq; a.Skv = d->Skv; a.H = d->H;
   a.scale = d->scale;
+  a.workspace = d->workspace;
+  a.workspace_bytes = d->workspace && d->workspace_bytes > 0 ? (size_t)d->workspace_bytes : 0;
   RGE_LAUNCH(launch_attention(a, (cudaStream_t)stream));
   return RGE_OK;
 }
+
+int64_t rge_attention_workspace_bytes(int32_t H) { return H > 0 ? (int64_t)attention_workspace_bytes(H) : 0; }
 
 int rge_op_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, void* out, int64_t ldo,
                        int32_t M, int32_t D, void* stream) {
@@ -361,6 +365,9 @@ struct rge_handle {
   // only depends on the time embedding. The vectors of the first kModHeadBlocks blocks are computed on the caller's
   // stream; the rest runs on this side stream beside those blocks' tensor-bound GEMMs (its CTAs fit next to a GEMM
   // CTA: 16 KB of shared memory) and is joined before the first block that reads it.
+  // scratch for the K/V-split of a ragged last query tile (attention.cu); attention launches of one handle never overlap
+  void* attn_ws = nullptr;
+  size_t attn_ws_bytes = 0;
   cudaStream_t smod = nullptr;
   cudaEvent_t ev_temb = nullptr, ev_mod = nullptr;
   // RGE_GROUPED=1: steps whose GEMMs all take the 1-CTA path (REGION steps: few rows) launch the independent GEMMs of
@@ -488,8 +495,11 @@ struct StepRun {
   }
 
   // queries = rows [row0, row0 + n_rows) of the [text; image] sequence (default: all active rows)
-  int attention(bf16* kc, bf16* vc, cudaStream_t sa, int row0 = 0, int n_rows = -1) const {
+  // allow_split: the launcher may cut the ragged last query tile along K/V (not beside the capped MLP GEMM, which
+  // already fills the attention grid's second wave there)
+  int attention(bf16* kc, bf16* vc, cudaStream_t sa, int row0 = 0, int n_rows = -1, bool allow_split = true) const {
     AttnArgs at;
+    if (allow_split) { at.workspace = h->attn_ws; at.workspace_bytes = h->attn_ws_bytes; }
     at.Q = h->q + (size_t)row0 * D; at.ldq = D; at.K = kc; at.ldk = D; at.V = vc; at.ldv = D;
     at.O = h->big + (size_t)row0 * ldb; at.ldo = ldb;
     at.Sq = n_rows < 0 ? MA : n_rows; at.Skv = S; at.H = h->H;
@@ -658,7 +668,7 @@ struct StepRun {
         RGE_CUDA(cudaStreamWaitEvent(s2, h->ev_aux[2], 0));
       }
     }
-    RGE_TRY(attention(kc, vc, h->sattn));
+    RGE_TRY(attention(kc, vc, h->sattn, 0, -1, false));
     RGE_TRY(one(sT, mlp, idle_sms));
     RGE_CUDA(link(h->sattn, h->ev_attn, st));
     return RGE_OK;
@@ -858,6 +868,8 @@ int rge_create(const rge_config* cfg, rge_handle** out) {
     A(cudaEventCreateWithFlags(&h->ev_attn, cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
   }
+  h->attn_ws_bytes = attention_workspace_bytes(h->H);
+  A(cudaMalloc(&h->attn_ws, h->attn_ws_bytes));
   A(cudaStreamCreateWithFlags(&h->smod, cudaStreamNonBlocking));
   A(cudaEventCreateWithFlags(&h->ev_temb, cudaEventDisableTiming));
   A(cudaEventCreateWithFlags(&h->ev_mod, cudaEventDisableTiming));
@@ -889,6 +901,7 @@ int rge_destroy(rge_handle* h) {
   }
   if (h->ev_txt) cudaEventDestroy(h->ev_txt);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->attn_ws) cudaFree(h->attn_ws);
   if (h->smod) cudaStreamDestroy(h->smod);
   if (h->ev_temb) cudaEventDestroy(h->ev_temb);
   if (h->ev_mod) cudaEventDestroy(h->ev_mod);

@@ -54,7 +54,14 @@ struct AttnDev {
   long ldo;
   int Sq, Skv;
   float sl2;  // softmax scale * log2(e)
+  // 1-D grid: CTAs [0, n_main_x * H) own 256 query rows of one head and the whole K/V sequence; with n_split > 0 the
+  // LAST 256-row tile of every head is cut along K/V instead: CTA n_main_x * H + head * n_split + s streams K/V tiles
+  // [s * tiles_per_split, ...) and leaves un-normalised fp32 partials (O, running maximum, row sum) in `ws`.
+  int H, n_main_x, n_split, tiles_per_split;
+  float* ws;  // [H][n_split][256 rows][kWsRow]
 };
+constexpr int kMaxSplit = 8;
+constexpr int kWsRow = 128 + 4;   // floats per partial row (16-byte multiple): O[128], reference maximum (raw score units), row sum, pad
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -113,9 +120,16 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * 2 * kTile;
-  const int n_tiles = (p.Skv + kTile - 1) / kTile;
+  const int n_main = p.n_main_x * p.H;
+  const int bid = blockIdx.x;
+  const bool split = bid >= n_main;
+  const int head = split ? (bid - n_main) / p.n_split : bid / p.n_main_x;
+  const int part = split ? (bid - n_main) % p.n_split : 0;
+  const int q0 = (split ? p.n_main_x : bid % p.n_main_x) * 2 * kTile;
+  const int n_tiles_all = (p.Skv + kTile - 1) / kTile;
+  const int tile0 = split ? part * p.tiles_per_split : 0;                       // first K/V tile of this CTA
+  const int n_tiles = split ? min(p.tiles_per_split, n_tiles_all - tile0) : n_tiles_all;
+  const bool two = q0 + kTile < p.Sq;   // the second query tile has rows: otherwise its softmax group and MMAs are skipped
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q);
@@ -165,7 +179,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const CUtensorMap* map = (t & 1) ? &map_v : &map_k;
         for (int half = 0; half < 2; ++half)
           tma_load_2d(s_kv + slot * kTileBytes + half * kHalfBytes, map, &kv_full[slot], head * 128 + half * 64,
-                      (t >> 1) * kTile);
+                      (tile0 + (t >> 1)) * kTile);
       }
       __syncwarp();
     }
@@ -223,21 +237,24 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         __syncwarp();
       }
     };
+    // A K/V slot is handed back by the last MMA that reads it: group 1's, or group 0's when the CTA has one query tile.
     mbar_wait(q_full, 0);
     wait_kv(0);
-    issue_qk(0, 0, nullptr);
-    issue_qk(1, 0, &kv_empty[0]);
+    issue_qk(0, 0, two ? nullptr : &kv_empty[0]);
+    if (two) issue_qk(1, 0, &kv_empty[0]);
     for (int j = 0; j < n_tiles; ++j) {
       const int tv = 2 * j + 1, tk = 2 * j + 2;
       const bool more = j + 1 < n_tiles;
       wait_kv(tv);
-      issue_pv(0, tv, j > 0, j, nullptr);
+      issue_pv(0, tv, j > 0, j, two ? nullptr : &kv_empty[tv % kSlots]);
       if (more) {
         wait_kv(tk);
-        issue_qk(0, tk, nullptr);
+        issue_qk(0, tk, two ? nullptr : &kv_empty[tk % kSlots]);
       }
-      issue_pv(1, tv, j > 0, j, &kv_empty[tv % kSlots]);
-      if (more) issue_qk(1, tk, &kv_empty[tk % kSlots]);
+      if (two) {
+        issue_pv(1, tv, j > 0, j, &kv_empty[tv % kSlots]);
+        if (more) issue_qk(1, tk, &kv_empty[tk % kSlots]);
+      }
     }
   }
   } else {
@@ -252,10 +269,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const float sl2 = p.sl2;
     float m_run = -INFINITY, l_run = 0.f;
 
-    for (int j = 0; j < n_tiles; ++j) {
+    const int my_tiles = (grp == 0 || two) ? n_tiles : 0;   // a group without query rows has nothing to do
+    for (int j = 0; j < my_tiles; ++j) {
       mbar_wait(&s_full[grp], j & 1);
       tc_fence_after();
-      const int n_valid = min(kTile, p.Skv - j * kTile);
+      const int n_valid = min(kTile, p.Skv - (tile0 + j) * kTile);
       // the whole score row in registers: four 32-column TMEM loads in flight, one wait
       uint32_t v[128];
       tmem_ld32p(t_s, v);
@@ -346,11 +364,31 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       unpack2f(sum_b, sum2, sum3);
       l_run += (sum0 + sum1) + (sum2 + sum3);
     }
-    // epilogue: O_i / l -> bf16 -> global
+    if (my_tiles > 0) {
     mbar_wait(&o_bar[grp], (n_tiles - 1) & 1);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
     const bool valid = row < p.Sq;
+    if (split) {
+      // K/V-split CTA: un-normalised fp32 partials; attention_combine_kernel merges the n_split parts of a row
+      float* wrow = p.ws + ((size_t)(head * p.n_split + part) * 2 * kTile + (row - q0)) * kWsRow;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_o + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(wrow + c * 32);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) dst[t] = make_uint4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        }
+      }
+      if (valid) {
+        wrow[128] = m_run;
+        wrow[129] = l_run;
+      }
+    } else {
+    // epilogue: O_i / l -> bf16 -> global
+    const float inv = 1.0f / l_run;
     __nv_bfloat16* orow = p.O + (long)(valid ? row : 0) * p.ldo + head * 128;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -370,11 +408,32 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
       }
     }
+    }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// Merges the K/V-split partials of the last query tile of every head: one block per (row, head), one thread per
+// head-dim column. O = sum_s w_s O_s / sum_s w_s l_s with w_s = 2^((m_s - max m) * scale * log2 e).
+__global__ void __launch_bounds__(128)
+attention_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ O, long ldo, int q0, int n_split,
+                         float sl2) {
+  const int r = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  const float* base = ws + ((size_t)head * n_split * 2 * kTile + r) * kWsRow;
+  const size_t stride = (size_t)2 * kTile * kWsRow;
+  float m = -INFINITY;
+  for (int s = 0; s < n_split; ++s) m = fmaxf(m, base[s * stride + 128]);
+  float acc = 0.f, l = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float w = exp2f((base[s * stride + 128] - m) * sl2);
+    acc = fmaf(w, base[s * stride + d], acc);
+    l = fmaf(w, base[s * stride + 129], l);
+  }
+  O[(long)(q0 + r) * ldo + head * 128 + d] = __float2bfloat16_rn(acc / l);
 }
 
 }  // namespace
@@ -407,11 +466,46 @@ cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   p.ldo = a.ldo;
   p.Sq = a.Sq;
   p.Skv = a.Skv;
+  p.H = a.H;
   p.sl2 = a.scale * 1.4426950408889634f;
-  dim3 grid((a.Sq + 2 * kTile - 1) / (2 * kTile), a.H);
+  const int n_x = (a.Sq + 2 * kTile - 1) / (2 * kTile);
+  const int n_tiles = (a.Skv + kTile - 1) / kTile;
+  p.n_main_x = n_x;
+  p.n_split = 0;
+  p.tiles_per_split = 0;
+  p.ws = nullptr;
+  // K/V split of the last query tile. REGION steps have T + N_e = ~1600 query rows: 7 CTAs per head x 24 heads = 168
+  // CTAs on 148 SMs, i.e. TWO waves for 1.14 waves of work (237 us against 125 us for the 144 CTAs of the six full
+  // tiles). When the full tiles fit into one wave and the ragged last tile of every head is what spills over, that
+  // tile is cut into n_split K/V ranges: the grid becomes 144 + 24 x 6 CTAs of which the second group runs a sixth of
+  // the K/V sequence each, plus a small merge kernel. Needs the caller's workspace (attention_workspace_bytes).
+  int num_sms = 0;
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (a.workspace && tuning().attn_split != 0 && n_x >= 2 && (n_x - 1) * a.H <= num_sms && n_x * a.H > num_sms &&
+      n_tiles >= 8) {
+    int n_split = num_sms / a.H;
+    if (n_split > kMaxSplit) n_split = kMaxSplit;
+    if (n_split >= 2) {
+      const int per = (n_tiles + n_split - 1) / n_split;
+      n_split = (n_tiles + per - 1) / per;            // no empty part
+      if (n_split >= 2 && a.workspace_bytes >= attention_workspace_bytes(a.H)) {
+        p.n_main_x = n_x - 1;
+        p.n_split = n_split;
+        p.tiles_per_split = per;
+        p.ws = static_cast<float*>(a.workspace);
+      }
+    }
+  }
+  const int grid = p.n_main_x * a.H + p.n_split * a.H;
   table[poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || p.n_split == 0) return e;
+  const int q0 = p.n_main_x * 2 * kTile;
+  attention_combine_kernel<<<dim3(a.Sq - q0, a.H), 128, 0, stream>>>(p.ws, a.O, a.ldo, q0, p.n_split, p.sl2);
   return cudaGetLastError();
 }
+
+size_t attention_workspace_bytes(int H) { return (size_t)H * kMaxSplit * 2 * kTile * kWsRow * sizeof(float); }
 
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   int k = tuning().attn_kernel;

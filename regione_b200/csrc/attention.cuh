@@ -16,7 +16,13 @@ struct AttnArgs {
   long ldo = 0;
   int Sq = 0, Skv = 0, H = 0;
   float scale = 0.08838834764831845f;  // 1/sqrt(128)
+  // optional scratch (attention_workspace_bytes(H)) that lets the launcher cut the ragged last query tile of every
+  // head along K/V when that tile alone would cost a second wave of CTAs; not shared between concurrent launches
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
 };
+
+size_t attention_workspace_bytes(int H);
 
 // Dispatches on tuning().attn_kernel: 0 = attention.cu (128-row K/V tiles, P aliased onto S), 1 = attention64.cu
 // (64-row K/V tiles, P in TMEM columns of its own: Q K^T of the next tile overlaps the softmax of the current one).

@@ -18,6 +18,7 @@ inline int current_device() {
 
 struct Tuning {
   int attn_poly;     // RGE_ATTN_POLY:   exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
+  int attn_split;    // RGE_ATTN_SPLIT:  1 = K/V split of the ragged last query tile when it alone costs a second wave (default)
   int attn_kernel;   // RGE_ATTN_KERNEL: 0 = attention.cu, 1 = attention64.cu (decoupled pipeline), -1 = default
   int gemm_bn;       // RGE_GEMM_BN:     forced tile width of the 1-CTA GEMM, 0 = choose per launch
   int gemm2_bn;      // RGE_GEMM2_BN:    forced tile width of the CTA-pair GEMM (multiple of 16), 0 = choose per launch
@@ -37,6 +38,7 @@ inline Tuning& tuning() {
   static Tuning t = [] {
     Tuning x;
     x.attn_poly = env_int("RGE_ATTN_POLY", -1);
+    x.attn_split = env_int("RGE_ATTN_SPLIT", 1);
     x.attn_kernel = env_int("RGE_ATTN_KERNEL", -1);
     x.gemm_bn = env_int("RGE_GEMM_BN", 0);
     x.gemm2_bn = env_int("RGE_GEMM2_BN", 0);
@@ -55,6 +57,7 @@ inline Tuning& tuning() {
 inline bool set_tuning(const char* name, int value) {
   Tuning& t = tuning();
   if (!strcmp(name, "attn_poly")) t.attn_poly = value;
+  else if (!strcmp(name, "attn_split")) t.attn_split = value;
   else if (!strcmp(name, "attn_kernel")) t.attn_kernel = value;
   else if (!strcmp(name, "gemm_bn")) t.gemm_bn = value;
   else if (!strcmp(name, "gemm2_bn")) t.gemm2_bn = value;

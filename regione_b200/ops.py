@@ -60,12 +60,18 @@ def gemm_group(members):
 
 
 def set_option(name: str, value: int) -> None:
-    """Run-time tuning knob of the kernels (rge_set_option): "attn_kernel", "attn_poly", "gemm_bn", "gemm2_bn", "2cta_min_m",
+    """Run-time tuning knob of the kernels (rge_set_option): "attn_kernel", "attn_poly", "attn_split", "gemm_bn", "gemm2_bn", "2cta_min_m",
     "raster", "trim_last", "nvtx"."""
     check(_lib.load().rge_set_option(name.encode(), int(value)), f"rge_set_option({name})")
 
 
-def attention(q, k, v, heads: int, out=None, scale: float | None = None):
+def attention_workspace(heads: int, device="cuda"):
+    """Scratch that lets `attention` cut the ragged last query tile of every head along K/V (rge_attn_desc.workspace)."""
+    n = _lib.load().rge_attention_workspace_bytes(heads)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def attention(q, k, v, heads: int, out=None, scale: float | None = None, workspace=None):
     """q [Sq, H*128], k/v [Skv, H*128] -> out [Sq, H*128]."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -79,6 +85,8 @@ def attention(q, k, v, heads: int, out=None, scale: float | None = None):
     d.O, d.ldo = ptr(out), out.stride(0)
     d.Sq, d.Skv, d.H = q.shape[0], k.shape[0], heads
     d.scale = scale if scale is not None else 128 ** -0.5
+    if workspace is not None:
+        d.workspace, d.workspace_bytes = ptr(workspace), workspace.numel() * workspace.element_size()
     check(lib.rge_op_attention(C.byref(d), stream_ptr()), "rge_op_attention")
     return out
 

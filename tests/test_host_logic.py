@@ -123,7 +123,7 @@ def test_standin_scheduler_schedule():
 
 def test_c_abi_library_loads_and_exports_declared_symbols():
     lib = _lib.load()
-    assert lib.rge_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.rge_abi_version() == _lib.ABI_VERSION == 5
     header = open(os.path.join(ROOT, "include", "regione_b200.h")).read()
     declared = set(re.findall(r"\b(rge_[a-z0-9_]+)\s*\(", header))
     declared -= {"rge_handle"}

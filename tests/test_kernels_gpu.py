@@ -337,6 +337,43 @@ def test_attention_matches_the_reference_s_flash_attn_func(Sq, Skv, H, attn_kern
     assert rel_l2(o, ref) <= 6e-3
 
 
+@pytest.mark.parametrize("Sq,Skv,H", [(1576, 8704, 24), (1600, 4000, 24), (1700, 2100, 24), (1537, 1100, 24),
+                                      (300, 1300, 100)])
+def test_attention_kv_split_of_the_ragged_last_query_tile(Sq, Skv, H):
+    """With a workspace, when the full 256-row query tiles of all heads fit into one wave of the 148 SMs and the ragged
+    last tile alone would need a second one (REGION steps: 512 + 1064 rows x 24 heads = 144 + 24 CTAs), that tile is cut
+    along K/V (un-normalised fp32 partials, merge kernel): same tolerance against the exact softmax as the plain
+    kernel, close to it element-wise, rows of the full tiles bit-identical; late large keys exercise the merge of parts
+    with different reference maxima, a remainder above 128 rows the two-group split CTAs."""
+    from regione_b200 import ops
+    g = _gen(41)
+    q = torch.randn(Sq, H * 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(Skv, H * 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(Skv, H * 128, device="cuda", generator=g).bfloat16()
+    k[Skv // 2:] *= 3.0
+    plain = ops.attention(q, k, v, H)
+    ws = ops.attention_workspace(H)
+    wide = torch.full((Sq, H * 128 + 256), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, H, out=wide, workspace=ws)
+    torch.cuda.synchronize()
+    got = wide[:, : H * 128]
+    assert bool((wide[:, H * 128:] == 7.0).all())
+    n_full = (Sq - 1) // 256 * 256
+    assert torch.equal(got[:n_full], plain[:n_full])
+    assert torch.isfinite(got.float()).all()
+    assert rel_l2(got[n_full:], plain[n_full:]) <= 6e-3            # two roundings of the same softmax
+    heads = slice(0, 2 * 128)                                       # exact reference on two heads (memory)
+    hd = lambda t: t[:, heads].reshape(1, -1, 2, 128).transpose(1, 2)   # noqa: E731
+    ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
+    assert rel_l2(got[:, heads], ref) <= 6e-3
+    ops.set_option("attn_split", 0)
+    try:
+        off = ops.attention(q, k, v, H, workspace=ws)
+    finally:
+        ops.set_option("attn_split", 1)
+    assert torch.equal(off, plain)
+
+
 def test_attention_strided_output_and_row_independence(attn_kernel):
     """Output written into a wider buffer (the engine's [S, D + 4D] layout); untouched columns stay untouched and
     each query row depends only on its own query (permutation equivariance)."""
