@@ -455,7 +455,6 @@ struct StepRun {
   bf16 *x_img, *n_img_p, *big_img;
   int idle_sms;             // SMs the last (partial) wave of the attention grid leaves idle
   bool fill_tail;           // ... and whether the single blocks' MLP-up GEMM runs there beside attention
-  int tail_cols;            // ... or, when the whole GEMM does not fit there, how many of its output columns do
 
   StepRun(rge_handle* h_, cudaStream_t st_, int pass_, int T_, int M_)
       : h(h_), st(st_), pass(pass_), D(h_->D), Dm(h_->Dm), T(T_), S(T_ + h_->L + h_->C), M(M_), MA(T_ + M_) {
@@ -476,15 +475,6 @@ struct StepRun {
     idle_sms = attn_tail ? h->num_sms - attn_tail : 0;
     const double attn_cta_flop = 4.0 * 256.0 * S * 128.0;
     fill_tail = fan && h->fill_attn_tail && idle_sms >= 16 && 2.0 * MA * (double)Dm * D / idle_sms <= 1.3 * attn_cta_flop;
-    // FULL steps: 816 attention CTAs = 5.51 waves; the 72 SMs the last wave leaves idle take as many 256-column
-    // blocks of the MLP-up GEMM as fit into one attention-CTA time (the rest of the GEMM runs before attention)
-    tail_cols = 0;
-    if (fan && h->fill_attn_tail && !fill_tail && idle_sms >= 16) {
-      const double per_col = 2.0 * MA * (double)D;
-      long cols = (long)(0.9 * idle_sms * attn_cta_flop / per_col) / 256 * 256;
-      if (cols > Dm - 256) cols = (Dm - 256) / 256 * 256;
-      tail_cols = cols >= 256 && Dm % 256 == 0 ? (int)cols : 0;
-    }
   }
 
   // makes `to` wait for everything enqueued on `from` so far
@@ -673,15 +663,6 @@ struct StepRun {
     RGE_CUDA(link(h->sattn, h->ev_attn, st));
     return RGE_OK;
   }
-  // columns [c0, c0 + n) of the single block's MLP-up GEMM
-  GemmArgs s_mlp_cols(int b, int c0, int n) const {
-    GemmArgs a = s_mlp(b);
-    a.W = a.W + (size_t)c0 * a.ldw;
-    if (a.bias) a.bias += c0;
-    a.col_off += c0;
-    a.N = n;
-    return a;
-  }
 
   // adaLN vectors of a single block at mod: shift, scale, gate
   int single_block_fanout(int b, int layer, const bf16* mod) const {
@@ -707,7 +688,7 @@ struct StepRun {
     RGE_TRY(one(st, s_q(b)));
     RGE_TRY(one(sK, s_k(b, kc)));
     RGE_TRY(one(sV, s_v(b, vc)));
-    if (!fill_tail && tail_cols == 0) {
+    if (!fill_tail) {
       // the MLP GEMM (independent of attention, disjoint columns of `big`) may still be running on sT when attention
       // starts: its CTAs and the attention CTAs share the SMs, which fills the partial last wave of either kernel
       RGE_TRY(one(sT, s_mlp(b)));
@@ -715,11 +696,9 @@ struct StepRun {
       RGE_CUDA(link(sV, h->ev_aux[2], st));
       RGE_TRY(attention(kc, vc, st));
     } else {
-      // whole GEMM beside attention (REGION steps), or its first columns before and its last `tail_cols` beside it
-      if (!fill_tail) RGE_TRY(one(sT, s_mlp_cols(b, 0, Dm - tail_cols)));
       RGE_CUDA(cudaEventRecord(h->ev_aux[1], sK));
       RGE_CUDA(cudaEventRecord(h->ev_aux[2], sV));
-      RGE_TRY(attention_beside_mlp(fill_tail ? s_mlp(b) : s_mlp_cols(b, Dm - tail_cols, tail_cols), kc, vc, true));
+      RGE_TRY(attention_beside_mlp(s_mlp(b), kc, vc, true));
     }
     RGE_CUDA(link(sT, h->ev_aux[0], st));
     return one(st, s_out(b, mod + 2 * D));

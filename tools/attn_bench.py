@@ -49,6 +49,8 @@ def main():
         res["ours kernel=attention64"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
         ops.set_option("attn_kernel", -1)
         res["ours default"] = sustained(lambda: ops.attention(q, k, v, H, out=o), secs)
+        ws = ops.attention_workspace(H)     # lets the launcher cut a ragged last query tile along K/V (REGION shapes)
+        res["ours default + workspace"] = sustained(lambda: ops.attention(q, k, v, H, out=o, workspace=ws), secs)
         try:
             from flash_attn import flash_attn_func
             q4, k4, v4 = q.view(1, Sq, H, 128), k.view(1, Skv, H, 128), v.view(1, Skv, H, 128)
