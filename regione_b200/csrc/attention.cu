@@ -54,12 +54,26 @@ struct AttnDev {
   long ldo;
   int Sq, Skv;
   float sl2;  // softmax scale * log2(e)
-  // 1-D grid: CTAs [0, n_main_x * H) own 256 query rows of one head and the whole K/V sequence; with n_split > 0 the
-  // LAST 256-row tile of every head is cut along K/V instead: CTA n_main_x * H + head * n_split + s streams K/V tiles
-  // [s * tiles_per_split, ...) and leaves un-normalised fp32 partials (O, running maximum, row sum) in `ws`.
-  int H, n_main_x, n_split, tiles_per_split;
-  float* ws;  // [H][n_split][256 rows][kWsRow]
+  // Work units = (256-row query tile, head): the n_full_x full tiles of every head first (head-major), then the ragged
+  // last tile of every head (Sq % 256 rows, if any). 1-D grid: CTAs [0, n_whole) run one unit over the whole K/V
+  // sequence; the remaining units - the ones that would form a mostly empty last wave of CTAs - are cut along K/V:
+  // CTA n_whole + u * n_split + s streams K/V tiles [s * tiles_per_split, ...) of unit n_whole + u and leaves
+  // un-normalised fp32 partials (O, reference maximum, row sum) in `ws` for attention_combine_kernel.
+  int H, n_full_x, n_whole, n_split, tiles_per_split;
+  float* ws;  // [split unit][n_split][256 rows][kWsRow]
 };
+
+// (query tile index within the head, head) of a work unit
+__device__ __forceinline__ void unit_decode(int unit, int n_full_x, int H, int& qx, int& head) {
+  const int n_full = n_full_x * H;
+  if (unit < n_full) {
+    head = unit / n_full_x;
+    qx = unit - head * n_full_x;
+  } else {
+    head = unit - n_full;
+    qx = n_full_x;
+  }
+}
 constexpr int kMaxSplit = 8;
 constexpr int kWsRow = 128 + 4;   // floats per partial row (16-byte multiple): O[128], reference maximum (raw score units), row sum, pad
 
@@ -120,12 +134,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_main = p.n_main_x * p.H;
   const int bid = blockIdx.x;
-  const bool split = bid >= n_main;
-  const int head = split ? (bid - n_main) / p.n_split : bid / p.n_main_x;
-  const int part = split ? (bid - n_main) % p.n_split : 0;
-  const int q0 = (split ? p.n_main_x : bid % p.n_main_x) * 2 * kTile;
+  const bool split = bid >= p.n_whole;
+  const int s_unit = split ? (bid - p.n_whole) / p.n_split : 0;                 // index among the split units
+  const int part = split ? (bid - p.n_whole) - s_unit * p.n_split : 0;
+  int qx, head;
+  unit_decode(split ? p.n_whole + s_unit : bid, p.n_full_x, p.H, qx, head);
+  const int q0 = qx * 2 * kTile;
   const int n_tiles_all = (p.Skv + kTile - 1) / kTile;
   const int tile0 = split ? part * p.tiles_per_split : 0;                       // first K/V tile of this CTA
   const int n_tiles = split ? min(p.tiles_per_split, n_tiles_all - tile0) : n_tiles_all;
@@ -370,7 +385,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const bool valid = row < p.Sq;
     if (split) {
       // K/V-split CTA: un-normalised fp32 partials; attention_combine_kernel merges the n_split parts of a row
-      float* wrow = p.ws + ((size_t)(head * p.n_split + part) * 2 * kTile + (row - q0)) * kWsRow;
+      float* wrow = p.ws + ((size_t)(s_unit * p.n_split + part) * 2 * kTile + (row - q0)) * kWsRow;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -417,13 +432,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// Merges the K/V-split partials of the last query tile of every head: one block per (row, head), one thread per
-// head-dim column. O = sum_s w_s O_s / sum_s w_s l_s with w_s = 2^((m_s - max m) * scale * log2 e).
+// Merges the K/V-split partials: one block per (row of the tile, split unit), one thread per head-dim column.
+// O = sum_s w_s O_s / sum_s w_s l_s with w_s = 2^((m_s - max m) * scale * log2 e).
 __global__ void __launch_bounds__(128)
-attention_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ O, long ldo, int q0, int n_split,
-                         float sl2) {
-  const int r = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
-  const float* base = ws + ((size_t)head * n_split * 2 * kTile + r) * kWsRow;
+attention_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ O, long ldo, int Sq, int H,
+                         int n_full_x, int n_whole, int n_split, float sl2) {
+  const int r = blockIdx.x, s_unit = blockIdx.y, d = threadIdx.x;
+  int qx, head;
+  unit_decode(n_whole + s_unit, n_full_x, H, qx, head);
+  const int row = qx * 2 * kTile + r;
+  if (row >= Sq) return;
+  const float* base = ws + ((size_t)s_unit * n_split * 2 * kTile + r) * kWsRow;
   const size_t stride = (size_t)2 * kTile * kWsRow;
   float m = -INFINITY;
   for (int s = 0; s < n_split; ++s) m = fmaxf(m, base[s * stride + 128]);
@@ -433,7 +452,7 @@ attention_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict
     acc = fmaf(w, base[s * stride + d], acc);
     l = fmaf(w, base[s * stride + 129], l);
   }
-  O[(long)(q0 + r) * ldo + head * 128 + d] = __float2bfloat16_rn(acc / l);
+  O[(long)row * ldo + head * 128 + d] = __float2bfloat16_rn(acc / l);
 }
 
 }  // namespace
@@ -470,42 +489,60 @@ cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   p.sl2 = a.scale * 1.4426950408889634f;
   const int n_x = (a.Sq + 2 * kTile - 1) / (2 * kTile);
   const int n_tiles = (a.Skv + kTile - 1) / kTile;
-  p.n_main_x = n_x;
+  const int n_units = n_x * a.H;
+  p.n_full_x = a.Sq / (2 * kTile);
+  p.n_whole = n_units;
   p.n_split = 0;
   p.tiles_per_split = 0;
   p.ws = nullptr;
-  // K/V split of the last query tile. REGION steps have T + N_e = ~1600 query rows: 7 CTAs per head x 24 heads = 168
-  // CTAs on 148 SMs, i.e. TWO waves for 1.14 waves of work (237 us against 125 us for the 144 CTAs of the six full
-  // tiles). When the full tiles fit into one wave and the ragged last tile of every head is what spills over, that
-  // tile is cut into n_split K/V ranges: the grid becomes 144 + 24 x 6 CTAs of which the second group runs a sixth of
-  // the K/V sequence each, plus a small merge kernel. Needs the caller's workspace (attention_workspace_bytes).
+  // K/V split of the units that would form the last, mostly empty wave of CTAs. REGION steps: ~1600 query rows = 7 tiles
+  // per head x 24 heads = 168 CTAs on 148 SMs, i.e. TWO waves for 1.14 waves of work (237 us against 125 us for one
+  // wave); FULL steps: 816 CTAs = 5.51 waves. The r = units % SMs trailing units (the ragged tiles come last in unit
+  // order: their partials are small) are cut into s K/V ranges each, s chosen to minimise
+  //   ceil(r s / SMs) / s  +  0.02 s        (waves of 1/s-length CTAs + per-CTA prologue, in full-CTA times)
+  // subject to r s <= 2 SMs (workspace bound); no split unless that beats the unsplit last wave by 10 %. Needs the
+  // caller's workspace (attention_workspace_bytes).
   int num_sms = 0;
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (a.workspace && tuning().attn_split != 0 && n_x >= 2 && (n_x - 1) * a.H <= num_sms && n_x * a.H > num_sms &&
-      n_tiles >= 8) {
-    int n_split = num_sms / a.H;
-    if (n_split > kMaxSplit) n_split = kMaxSplit;
-    if (n_split >= 2) {
-      const int per = (n_tiles + n_split - 1) / n_split;
-      n_split = (n_tiles + per - 1) / per;            // no empty part
-      if (n_split >= 2 && a.workspace_bytes >= attention_workspace_bytes(a.H)) {
-        p.n_main_x = n_x - 1;
+  const int r = num_sms > 0 ? n_units % num_sms : 0;
+  if (a.workspace && tuning().attn_split != 0 && r > 0 && n_tiles >= 8 &&
+      a.workspace_bytes >= attention_workspace_bytes(a.H)) {
+    int best_s = 0;
+    double best = 0.9;
+    for (int sp = 2; sp <= kMaxSplit && r * sp <= 2 * num_sms; ++sp) {
+      const double cost = (double)((r * sp + num_sms - 1) / num_sms) / sp + 0.02 * sp;
+      if (cost < best) { best = cost; best_s = sp; }
+    }
+    if (best_s >= 2) {
+      const int per = (n_tiles + best_s - 1) / best_s;
+      const int n_split = (n_tiles + per - 1) / per;            // no empty part
+      if (n_split >= 2) {
+        p.n_whole = n_units - r;
         p.n_split = n_split;
         p.tiles_per_split = per;
         p.ws = static_cast<float*>(a.workspace);
       }
     }
   }
-  const int grid = p.n_main_x * a.H + p.n_split * a.H;
+  const int n_split_units = n_units - p.n_whole;
+  const int grid = p.n_whole + n_split_units * p.n_split;
   table[poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || p.n_split == 0) return e;
-  const int q0 = p.n_main_x * 2 * kTile;
-  attention_combine_kernel<<<dim3(a.Sq - q0, a.H), 128, 0, stream>>>(p.ws, a.O, a.ldo, q0, p.n_split, p.sl2);
+  attention_combine_kernel<<<dim3(2 * kTile, n_split_units), 128, 0, stream>>>(p.ws, a.O, a.ldo, a.Sq, a.H, p.n_full_x,
+                                                                              p.n_whole, p.n_split, p.sl2);
   return cudaGetLastError();
 }
 
-size_t attention_workspace_bytes(int H) { return (size_t)H * kMaxSplit * 2 * kTile * kWsRow * sizeof(float); }
+// Upper bound of the scratch a launch may use: at most 2 x SMs split CTAs, each with 256 partial rows.
+size_t attention_workspace_bytes(int H) {
+  (void)H;
+  int dev = 0, num_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (num_sms <= 0) num_sms = 148;
+  return (size_t)2 * num_sms * 2 * kTile * kWsRow * sizeof(float);
+}
 
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   int k = tuning().attn_kernel;

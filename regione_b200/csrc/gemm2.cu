@@ -67,7 +67,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
   tc_fence_before();
   cluster_sync_all();
-  __syncthreads();   // redundant after the cluster barrier; compute-sanitizer racecheck only models the CTA barrier
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

@@ -338,13 +338,14 @@ def test_attention_matches_the_reference_s_flash_attn_func(Sq, Skv, H, attn_kern
 
 
 @pytest.mark.parametrize("Sq,Skv,H", [(1576, 8704, 24), (1600, 4000, 24), (1700, 2100, 24), (1537, 1100, 24),
-                                      (300, 1300, 100)])
-def test_attention_kv_split_of_the_ragged_last_query_tile(Sq, Skv, H):
-    """With a workspace, when the full 256-row query tiles of all heads fit into one wave of the 148 SMs and the ragged
-    last tile alone would need a second one (REGION steps: 512 + 1064 rows x 24 heads = 144 + 24 CTAs), that tile is cut
-    along K/V (un-normalised fp32 partials, merge kernel): same tolerance against the exact softmax as the plain
-    kernel, close to it element-wise, rows of the full tiles bit-identical; late large keys exercise the merge of parts
-    with different reference maxima, a remainder above 128 rows the two-group split CTAs."""
+                                      (300, 1300, 100), (2048, 1300, 20), (872, 2100, 24), (4864, 4864, 24)])
+def test_attention_kv_split_of_the_trailing_work_units(Sq, Skv, H):
+    """With a workspace, the (256-row query tile, head) units that would form the last, mostly empty wave of CTAs on the
+    148 SMs are cut along K/V (un-normalised fp32 partials, merge kernel) - REGION steps: 512 + 1064 rows x 24 heads =
+    148 + 20 units, the ragged 40-row tiles last; (2048, ., 20): full tiles get split; (872, ., 24): every unit is split.
+    Same tolerance against the exact softmax as the plain kernel and close to it element-wise; late large keys
+    exercise the merge of parts with different reference maxima, a ragged tile above 128 rows the two-group split
+    CTAs; `attn_split` = 0 gives the plain kernel back bit for bit."""
     from regione_b200 import ops
     g = _gen(41)
     q = torch.randn(Sq, H * 128, device="cuda", generator=g).bfloat16()
@@ -358,11 +359,10 @@ def test_attention_kv_split_of_the_ragged_last_query_tile(Sq, Skv, H):
     torch.cuda.synchronize()
     got = wide[:, : H * 128]
     assert bool((wide[:, H * 128:] == 7.0).all())
-    n_full = (Sq - 1) // 256 * 256
-    assert torch.equal(got[:n_full], plain[:n_full])
     assert torch.isfinite(got.float()).all()
-    assert rel_l2(got[n_full:], plain[n_full:]) <= 6e-3            # two roundings of the same softmax
-    heads = slice(0, 2 * 128)                                       # exact reference on two heads (memory)
+    assert not torch.equal(got, plain)                              # the split path did run
+    assert rel_l2(got, plain) <= 6e-3                               # two roundings of the same softmax
+    heads = slice((H - 2) * 128, H * 128)                           # exact reference on the last two heads (split ones)
     hd = lambda t: t[:, heads].reshape(1, -1, 2, 128).transpose(1, 2)   # noqa: E731
     ref = of.exact_attention(hd(q), hd(k), hd(v))[0]
     assert rel_l2(got[:, heads], ref) <= 6e-3
