@@ -495,33 +495,28 @@ cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   p.n_split = 0;
   p.tiles_per_split = 0;
   p.ws = nullptr;
-  // K/V split of the units that would form the last, mostly empty wave of CTAs. REGION steps: ~1600 query rows = 7 tiles
-  // per head x 24 heads = 168 CTAs on 148 SMs, i.e. TWO waves for 1.14 waves of work (237 us against 125 us for one
-  // wave); FULL steps: 816 CTAs = 5.51 waves. The r = units % SMs trailing units (the ragged tiles come last in unit
-  // order: their partials are small) are cut into s K/V ranges each, s chosen to minimise
-  //   ceil(r s / SMs) / s  +  0.02 s        (waves of 1/s-length CTAs + per-CTA prologue, in full-CTA times)
-  // subject to r s <= 2 SMs (workspace bound); no split unless that beats the unsplit last wave by 10 %. Needs the
+  // K/V split of the units that would form a last, nearly empty wave of CTAs. REGION steps: ~1600 query rows = 7 tiles
+  // per head x 24 heads = 168 CTAs on 148 SMs, i.e. TWO waves for 1.14 waves of work (228 us against 125 us for one
+  // wave). The r = units % SMs trailing units (the ragged tiles come last in unit order: their partials are small) are
+  // cut into s = SMs / r K/V ranges, so that they run as ONE extra wave of 1/s-length CTAs. Only for r <= SMs / 4:
+  // measured (profiles/r02_attn_bench_session11_wide_split.log), a part costs ~6 us of prologue, partial stores and merge on top of
+  // its share of the K/V sequence, so 1576 x 8704 gains 21 % (r = 20, s = 7) and 4864^2 7 % (r = 12, s = 8), while
+  // the 3-way splits that r = 76 (8704^2: 5.51 waves) or r = 96 (872 rows) would need gain nothing or lose. Needs the
   // caller's workspace (attention_workspace_bytes).
   int num_sms = 0;
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   const int r = num_sms > 0 ? n_units % num_sms : 0;
-  if (a.workspace && tuning().attn_split != 0 && r > 0 && n_tiles >= 8 &&
+  if (a.workspace && tuning().attn_split != 0 && r > 0 && 4 * r <= num_sms && n_tiles >= 8 &&
       a.workspace_bytes >= attention_workspace_bytes(a.H)) {
-    int best_s = 0;
-    double best = 0.9;
-    for (int sp = 2; sp <= kMaxSplit && r * sp <= 2 * num_sms; ++sp) {
-      const double cost = (double)((r * sp + num_sms - 1) / num_sms) / sp + 0.02 * sp;
-      if (cost < best) { best = cost; best_s = sp; }
-    }
-    if (best_s >= 2) {
-      const int per = (n_tiles + best_s - 1) / best_s;
-      const int n_split = (n_tiles + per - 1) / per;            // no empty part
-      if (n_split >= 2) {
-        p.n_whole = n_units - r;
-        p.n_split = n_split;
-        p.tiles_per_split = per;
-        p.ws = static_cast<float*>(a.workspace);
-      }
+    int sp = num_sms / r;
+    if (sp > kMaxSplit) sp = kMaxSplit;
+    const int per = (n_tiles + sp - 1) / sp;
+    const int n_split = (n_tiles + per - 1) / per;            // no empty part
+    if (n_split >= 2) {
+      p.n_whole = n_units - r;
+      p.n_split = n_split;
+      p.tiles_per_split = per;
+      p.ws = static_cast<float*>(a.workspace);
     }
   }
   const int n_split_units = n_units - p.n_whole;
@@ -534,14 +529,14 @@ cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// Upper bound of the scratch a launch may use: at most 2 x SMs split CTAs, each with 256 partial rows.
+// Upper bound of the scratch a launch may use: at most one wave of split CTAs (r s <= SMs), each with 256 partial rows.
 size_t attention_workspace_bytes(int H) {
   (void)H;
   int dev = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (num_sms <= 0) num_sms = 148;
-  return (size_t)2 * num_sms * 2 * kTile * kWsRow * sizeof(float);
+  return (size_t)num_sms * 2 * kTile * kWsRow * sizeof(float);
 }
 
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
