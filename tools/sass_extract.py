@@ -50,7 +50,7 @@ def main():
             short = k.split("(")[0]
             f.write(f"{short}: {len(lines)} instructions; " + ", ".join(f"{w} {ops[w]}" for w in WATCH if ops[w]) +
                     f"; HMMA {ops['HMMA']}, HGMMA {ops['HGMMA']}\n")
-            if any(t in short for t in ("attention_kernel<0>", "attention_kernel<4>", "gemm2_kernel<3>", "gemm3_kernel",
+            if any(t in short for t in ("attention_kernel<2>", "attention_kernel<0>", "gemm2_kernel<3>", "gemm2_kernel<2>",
                                         "gemm_kernel<0>")):
                 fn = re.sub(r"[^A-Za-z0-9]+", "_", short).strip("_")
                 with open(os.path.join(out_dir, f"{prefix}_sass_{fn}.txt"), "w") as g:
