@@ -524,8 +524,11 @@ cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   table[poly == 0 ? 0 : poly - 1]<<<grid, kThreads, kSmemBytes, stream>>>(mq, mk, mv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || p.n_split == 0) return e;
-  attention_combine_kernel<<<dim3(2 * kTile, n_split_units), 128, 0, stream>>>(p.ws, a.O, a.ldo, a.Sq, a.H, p.n_full_x,
-                                                                              p.n_whole, p.n_split, p.sl2);
+  // rows to merge per split unit: the ragged tile's rows when only ragged tiles are split (REGION steps: 40 of 256)
+  const int ragged_rows = a.Sq - p.n_full_x * 2 * kTile;
+  const int rows = (ragged_rows > 0 && p.n_whole >= p.n_full_x * a.H) ? ragged_rows : 2 * kTile;
+  attention_combine_kernel<<<dim3(rows, n_split_units), 128, 0, stream>>>(p.ws, a.O, a.ldo, a.Sq, a.H, p.n_full_x,
+                                                                         p.n_whole, p.n_split, p.sl2);
   return cudaGetLastError();
 }
 
