@@ -12,10 +12,10 @@
 // itself, in TMEM) when a row maximum grows by more than 2^8.
 //
 // Measured and rejected in round 2 (profiles/r02_attn_bench_pipe_poly_variants.log, r02_ncu_attention_source_hotspots.txt):
-//   * evaluating 3-4 of every 8 exponential pairs as a packed-FFMA2 polynomial instead of MUFU.EX2 (`attn_poly` knob):
-//     no better than 2 of 8 (the default since the warp-uniform issue loops: 813 vs 829 us at 8704^2, 222 vs 237 us at
-//     1576 x 8704, profiles/r02_attn_bench_early_qk_variants.log); 4 of 8 is slower - the extra ~4 issue slots per
-//     offloaded score cost the single softmax warp per scheduler more than the MUFU time saves;
+//   * evaluating 4 of every 8 exponential pairs as a packed-FFMA2 polynomial instead of MUFU.EX2 (`attn_poly` knob):
+//     slower than 2 or 3 of 8 (3 is the default since the warp-uniform issue loops: 813 vs 829 us at 8704^2, 222 vs
+//     237 us at 1576 x 8704, profiles/r02_attn_bench_early_qk_variants.log) - beyond that the extra ~4 issue slots
+//     per offloaded score cost the single softmax warp per scheduler more than the MUFU time saves;
 //   * S = Q K^T and the softmax in two software-pipelined 64-column halves (own commit per half, half 1's TMEM loads in
 //     flight during half 0's exponentials): 17 % slower - TMEM reads are not a bottleneck (measured 720-920 B/clk/SM,
 //     profiles/r02_pipes_microbench.log) and the second barrier round trip per tile lengthens the serial
@@ -46,7 +46,7 @@ constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kSlots = 5;
 constexpr int kSmemBytes = 2 * kTileBytes + kSlots * kTileBytes + 256 + 1024;
 constexpr int kDefaultKernel = 0;       // 0: this file, 1: attention64.cu (RGE_ATTN_KERNEL overrides)
-constexpr int kDefaultPoly = 2;         // exponential pairs of every 8 on the FMA pipe (RGE_ATTN_POLY overrides)
+constexpr int kDefaultPoly = 3;         // exponential pairs of every 8 on the FMA pipe (RGE_ATTN_POLY overrides)
 constexpr uint32_t kColS = 0, kColO = 256;  // TMEM column bases: S_i at kColS + 128 i, O_i at kColO + 128 i
 
 struct AttnDev {
@@ -460,8 +460,8 @@ attention_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict
 cudaError_t launch_attention128(const AttnArgs& a, cudaStream_t stream) {
   if (a.Sq <= 0 || a.H <= 0) return cudaSuccess;
   if (a.Skv <= 0 || (a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
-  // tuning knob attn_poly / RGE_ATTN_POLY: 0, 2 (default, fastest measured), 3 or 4 of every 8 exponential pairs on the
-  // FMA pipe instead of MUFU
+  // tuning knob attn_poly / RGE_ATTN_POLY: 0, 2, 3 (default) or 4 of every 8 exponential pairs on the FMA pipe instead
+  // of MUFU (2 and 3 are within 1 % of each other, 3 ahead on the slower boxes: profiles/r02_attn_bench_final.log)
   int poly = tuning().attn_poly;
   if (poly < 0) poly = kDefaultPoly;
   if (poly != 2 && poly != 3 && poly != 4) poly = 0;
