@@ -94,7 +94,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
+      int m_blk, n_blk;
+      tile_decode(p, tile, num_m, num_n, m_blk, n_blk);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
@@ -145,7 +146,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int r = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
+      int m_blk, n_blk;
+      tile_decode(p, tile, num_m, num_n, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t use = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], use);
@@ -356,6 +358,7 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, cfg.bn)) return cudaErrorInvalidValue;
   GemmDev p = to_dev(a);
   p.n_fast = pick_n_fast(a);
+  p.n_group = p.n_fast ? pick_n_group(a, cfg.bn) : 0;
   const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + cfg.bn - 1) / cfg.bn);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, cfg);

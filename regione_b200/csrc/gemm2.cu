@@ -84,7 +84,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
+      int m_blk, n_blk;
+      tile_decode(p, tile, num_m, num_n, m_blk, n_blk);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
@@ -136,7 +137,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int r = q * 32 + lane;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int m_blk = p.n_fast ? tile / num_n : tile % num_m, n_blk = p.n_fast ? tile % num_n : tile / num_m;
+      int m_blk, n_blk;
+      tile_decode(p, tile, num_m, num_n, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t use = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], use);
@@ -188,6 +190,7 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, bn / 2)) return cudaErrorInvalidValue;
   GemmDev p = to_dev(a);
   p.n_fast = pick_n_fast(a);
+  p.n_group = p.n_fast ? pick_n_group(a, bn) : 0;
   const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + bn - 1) / bn);
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
   gemm2_kernel<EPI><<<2 * pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, bn);

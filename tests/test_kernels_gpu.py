@@ -117,6 +117,44 @@ def test_gemm_cta_pair_kernel_tile_widths_bit_identical(bn):
         assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("M", [2304 + 77, 600])   # CTA-pair kernel, 1-CTA kernel (28 % padding to 256 rows)
+@pytest.mark.parametrize("n_group", [1, 3, 5])
+def test_gemm_grouped_n_fast_tile_order_bit_identical(M, n_group):
+    """Tile orders only permute the tile list: walking down M, along N, and along N in groups of column blocks (the order
+    K-heavy launches use so that a slice of W stays in the L2, with a narrower last group) give bit-identical results,
+    on the CTA-pair and the 1-CTA kernel."""
+    from regione_b200 import _lib, ops
+    g = _gen(23)
+    N, K = 1792, 192
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    gate = torch.randn(N, device="cuda", generator=g).bfloat16()
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+
+    def run():
+        o = res.clone()
+        ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, gate=gate, res=o, out=o)
+        return ops.gemm(a, w, b), o
+
+    try:
+        ops.set_option("gemm2_bn", 256)
+        ops.set_option("gemm_bn", 128)
+        ops.set_option("raster", 0)
+        ref = run()
+        ops.set_option("raster", 1)
+        ops.set_option("n_group", 0)
+        plain = run()
+        ops.set_option("n_group", n_group)
+        got = run()
+    finally:
+        for k, v in (("raster", -1), ("n_group", -1), ("gemm2_bn", 0), ("gemm_bn", 0)):
+            ops.set_option(k, v)
+    assert rel_l2(ref[0], a.float() @ w.float().t() + b.float()) <= BF16_TOL
+    for x, y, z in zip(ref, plain, got):
+        assert torch.equal(x, y) and torch.equal(x, z)
+
+
 @pytest.fixture
 def one_cta_kernel():
     """Keeps every launch on the 1-CTA kernel (the per-shape rule would send well-filled REGION sizes to the CTA pair)."""
