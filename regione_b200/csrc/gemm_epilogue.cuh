@@ -61,19 +61,17 @@ inline int pick_n_fast(const GemmArgs& a) {
   return a_bytes > 96e6 && w_bytes < a_bytes ? 1 : 0;
 }
 
-// Column blocks per group for the N-fast order. Walking along N keeps one A band hot, but every wave of concurrent
-// tiles then streams the WHOLE of W, and 75 - 94 MB of W do not stay in the L2 next to the A bands (ncu, FF-down
-// 8192 x 3072 x 12288: 727 MB of DRAM reads for 277 MB of operands - W is re-read once per wave). Sweeping the row
-// bands once per group of column blocks whose W slice (<= 48 MB) does stay resident reads A once per group and W
-// once: 2 x 201 + 75 = 478 MB for that launch. RGE_N_GROUP: 0 = no grouping, n = forced group size.
+// Column blocks per group for the N-fast order (0 = no grouping, the default). Walking along N keeps one A band hot, but
+// every wave of concurrent tiles then streams the WHOLE of W, and 75 - 94 MB of W do not stay in the L2 next to the A
+// bands (ncu, FF-down 8192 x 3072 x 12288: 809 MB of DRAM reads for 277 MB of operands). Sweeping the row bands once
+// per group of column blocks whose W slice would fit was measured and REJECTED: the slice does not stay resident
+// either (781 MB, and 1 - 2 % slower, profiles/r02_n_group_l2_hints_rejected.log); pinning it with evict-last TMA
+// hints and streaming A evict-first loses the A band's reuse across the group (1011 MB, 9 % slower). These launches
+// run at 94 % tensor-pipe activity regardless. RGE_N_GROUP = n forces a group size (tests).
 inline int pick_n_group(const GemmArgs& a, int bn) {
+  (void)a; (void)bn;
   const int forced = tuning().n_group;
-  if (forced >= 0) return forced;
-  const int num_n = (a.N + bn - 1) / bn;
-  const double w_bytes = 2.0 * a.N * a.K;
-  const int groups = (int)((w_bytes + 48e6 - 1) / 48e6);
-  if (groups <= 1) return 0;
-  return (num_n + groups - 1) / groups;
+  return forced > 0 ? forced : 0;
 }
 
 inline GemmDev to_dev(const GemmArgs& a) {

@@ -24,7 +24,7 @@ struct Tuning {
   int gemm2_bn;      // RGE_GEMM2_BN:    forced tile width of the CTA-pair GEMM (multiple of 16), 0 = choose per launch
   int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never, -1 = per-shape rule (default)
   int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
-  int n_group;       // RGE_N_GROUP:     column blocks per group of the N-fast tile order, 0 = no grouping, -1 = per launch
+  int n_group;       // RGE_N_GROUP:     column blocks per group of the N-fast tile order (tests; measured and rejected), <= 0 = none
   int trim_last;     // RGE_TRIM_LAST:   1 = the last block computes only the rows whose output is kept (default)
   int split_mod;     // RGE_SPLIT_MOD:   1 = modulation GEMV of all but the first blocks on a side stream (default)
   int nvtx;          // RGE_NVTX:        1 = NVTX ranges per step / block / stage (profilers only)
