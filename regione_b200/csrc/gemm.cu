@@ -358,7 +358,6 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, cfg.bn)) return cudaErrorInvalidValue;
   GemmDev p = to_dev(a);
   p.n_fast = pick_n_fast(a);
-  p.n_group = p.n_fast ? pick_n_group(a, cfg.bn) : 0;
   const int num_tiles = ((a.M + BM - 1) / BM) * ((a.N + cfg.bn - 1) / cfg.bn);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, cfg);

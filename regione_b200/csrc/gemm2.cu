@@ -31,10 +31,22 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 constexpr int kTmemCols = 512;
 
+// What a launch works on. Whole tiles: work items [0, end) are tiles of the tile order. Split tail (split > 1): work
+// item w is K-range  w % split  of tile  tile_base + w / split ; its fp32 accumulators go to `ws` (one 256 x 256 slab
+// per work item) instead of through the epilogue, and gemm2_finish_kernel sums the slabs and applies the epilogue.
+struct WorkRange {
+  int end;
+  int split;
+  int kb_per;      // k-blocks per K-range
+  int tile_base;
+  float* ws;
+};
+constexpr int kSlabFloats = 2 * BM * BN;
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmDev p,
-             const int bn) {
+             const int bn, const WorkRange wr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -72,10 +84,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
   const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_n = (p.N + bn - 1) / bn;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb_all = (p.K + BK - 1) / BK;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
+  // work item -> tile, first k-block, number of k-blocks
+  constexpr bool kCanSplit = EPI != EPI_NORM_ROPE;     // that epilogue owns whole heads and needs every register
+  auto decode = [&](int w, int& tile, int& kb0, int& nkb) {
+    if (!kCanSplit || wr.split <= 1) {
+      tile = w; kb0 = 0; nkb = num_kb_all;
+    } else {
+      tile = wr.tile_base + w / wr.split;
+      kb0 = (w % wr.split) * wr.kb_per;
+      nkb = min(wr.kb_per, num_kb_all - kb0);
+    }
+  };
 
   // Producer and issuer warps loop with all lanes and elect one lane per asynchronous instruction group (see gemm.cu:
   // a divergent `if (lane == 0)` region costs ~75 issue slots per k-block in ELECT / BRA.U.ANY loops and R2UR moves).
@@ -83,10 +105,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     // ------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      int m_blk, n_blk;
+    for (int w = pair; w < wr.end; w += num_pairs) {
+      int tile, kb0, nkb, m_blk, n_blk;
+      decode(w, tile, kb0, nkb);
       tile_decode(p, tile, num_m, num_n, m_blk, n_blk);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb0 + nkb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * kStageBytes;
@@ -108,7 +131,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      for (int w = pair; w < wr.end; w += num_pairs, ++it) {
+        int tile, kb0, num_kb;
+        decode(w, tile, kb0, num_kb);
         const int acc = it & 1;
         const uint32_t use = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], use ^ 1);
@@ -136,22 +161,101 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int q = warp & 3;
     const int r = q * 32 + lane;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      int m_blk, n_blk;
+    for (int w = pair; w < wr.end; w += num_pairs, ++it) {
+      int tile, kb0, nkb, m_blk, n_blk;
+      decode(w, tile, kb0, nkb);
       tile_decode(p, tile, num_m, num_n, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t use = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], use);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      gemm_epilogue_row<EPI, true>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * bn, bn,
-                                   TmemRelease{&tempty_bar[acc], 0});
+      const TmemRelease release{&tempty_bar[acc], 0};
+      if (!kCanSplit || wr.split <= 1) {
+        gemm_epilogue_row<EPI, true>(p, taddr, m_blk * 2 * BM + (int)rank * BM + r, n_blk * bn, bn, release);
+      } else if constexpr (kCanSplit) {
+        // raw fp32 accumulators of this K-range into the work item's slab, row-major [256][BN]
+        float* dst = wr.ws + (size_t)w * kSlabFloats + (size_t)((int)rank * BM + r) * BN;
+#pragma unroll 1
+        for (int c = 0; c < bn; c += 16) {
+          uint32_t v[16];
+          tmem_ld16p(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            reinterpret_cast<uint4*>(dst + c)[t] = make_uint4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        }
+        release();
+      }
     }
   }
 
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
+// Second half of a split tail: sums the K-range slabs of a tile in a fixed order and applies the epilogue with the
+// same code the fused path runs (epilogue_chunk), 8 columns per thread, 8 rows per block.
+template <int EPI>
+__global__ void __launch_bounds__(256)
+gemm2_finish_kernel(const GemmDev p, const int bn, const WorkRange wr) {
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (p.N + bn - 1) / bn;
+  const int t_idx = blockIdx.x / 32;                                   // tail tile
+  const int row = (blockIdx.x % 32) * 8 + (threadIdx.x >> 5);         // row of the 256-row tile
+  const int col = (threadIdx.x & 31) * 8;                              // first of this thread's 8 columns
+  int m_blk, n_blk;
+  tile_decode(p, wr.tile_base + t_idx, num_m, num_n, m_blk, n_blk);
+  const int m = m_blk * 2 * BM + row, n0 = n_blk * bn + col;
+  if (col >= bn || n0 >= p.N) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < wr.split; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(wr.ws + (size_t)(t_idx * wr.split + s) * kSlabFloats +
+                                                        (size_t)row * BN + col);
+    const float4 x = src[0], y = src[1];
+    acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+    acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+  }
+  const bool valid = m < p.M;
+  const long out_row = valid ? (long)((p.row_map ? __ldg(p.row_map + m) : m) + p.row_off) : 0;
+  __nv_bfloat16* out_ptr = p.out + out_row * p.ldo + p.col_off;
+  uint32_t v[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(acc[j]);
+  uint4 rv[4];
+  load_residual<EPI, 1>(p, rv, m, n0, valid);
+  epilogue_chunk<EPI, 1>(p, v, rv, out_ptr, n0, valid);
+}
+
+// Split of the last, partial wave of tiles along K. With 74 pairs the K-heavy launches of a FULL step leave their last
+// wave mostly empty (FF-down 8192 x 3072 x 12288: 384 tiles = 5.19 waves of 65-us tiles). The R = tiles mod pairs
+// trailing tiles are cut into S K-ranges each (S <= 4, chosen like the attention split: ceil(R S / pairs) / S + 0.04 S
+// full-tile times against 1), computed by a second launch of the same kernel on a library-owned side stream - its CTAs
+// become resident as the whole-tile launch drains - and finished by gemm2_finish_kernel. No in-kernel spinning on
+// other CTAs. Only for K >= 6144 (the slabs cost ~8 us) and not for EPI_NORM_ROPE (its epilogue owns whole heads).
+struct SplitRes {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+};
+SplitRes* split_resources(int max_pairs) {
+  static SplitRes res[kMaxDevices];
+  SplitRes& r = res[current_device()];
+  if (!r.side) {
+    const size_t n = (size_t)2 * max_pairs * kSlabFloats;
+    if (cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.ev_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc(&r.ws, n * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      r.side = nullptr;
+      return nullptr;
+    }
+    r.ws_floats = n;
+  }
+  return &r;
 }
 
 // Tile width: minimise  ceil(tiles / pairs) x (bn + 60) [x 1.04 for odd multiples of 16]  over the multiples of 16 (of
@@ -190,11 +294,42 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, bn / 2)) return cudaErrorInvalidValue;
   GemmDev p = to_dev(a);
   p.n_fast = pick_n_fast(a);
-  p.n_group = p.n_fast ? pick_n_group(a, bn) : 0;
   const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + bn - 1) / bn);
-  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  gemm2_kernel<EPI><<<2 * pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, bn);
-  return cudaGetLastError();
+  const int num_kb = (a.K + BK - 1) / BK;
+  // split of the trailing partial wave along K (see SplitRes)
+  int split = 1;
+  const int tail = num_tiles % max_pairs;
+  if (EPI != EPI_NORM_ROPE && tuning().split_tail && num_kb >= 96 && tail > 0) {
+    double best = 0.85;
+    for (int sp = 2; sp <= 4 && tail * sp <= 2 * max_pairs && num_kb / sp >= 16; ++sp) {
+      const double cost = (double)((tail * sp + max_pairs - 1) / max_pairs) / sp + 0.04 * sp;
+      if (cost < best) { best = cost; split = sp; }
+    }
+  }
+  SplitRes* res = split > 1 ? split_resources(max_pairs) : nullptr;
+  if (!res) {
+    const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+    gemm2_kernel<EPI><<<2 * pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, bn,
+                                                                   WorkRange{num_tiles, 1, 0, 0, nullptr});
+    return cudaGetLastError();
+  }
+  const int full = num_tiles - tail;
+  const int kb_per = (num_kb + split - 1) / split;
+  const int parts = (num_kb + kb_per - 1) / kb_per;          // no empty K-range
+  const WorkRange tail_wr{tail * parts, parts, kb_per, full, res->ws};
+  cudaError_t e = cudaEventRecord(res->ev_in, stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(res->side, res->ev_in, 0);
+  if (e != cudaSuccess) return e;
+  if (full > 0)
+    gemm2_kernel<EPI><<<2 * max_pairs, kThreads, kSmemBytes, stream>>>(map_a, map_b, p, bn,
+                                                                       WorkRange{full, 1, 0, 0, nullptr});
+  const int tail_pairs = tail_wr.end < max_pairs ? tail_wr.end : max_pairs;
+  gemm2_kernel<EPI><<<2 * tail_pairs, kThreads, kSmemBytes, res->side>>>(map_a, map_b, p, bn, tail_wr);
+  gemm2_finish_kernel<EPI><<<tail * 32, 256, 0, res->side>>>(p, bn, tail_wr);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaEventRecord(res->ev_out, res->side);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, res->ev_out, 0);
+  return e;
 }
 
 }  // namespace

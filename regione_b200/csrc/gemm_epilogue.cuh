@@ -26,26 +26,12 @@ struct GemmDev {
   long rope_ld;   // 0: rope_cs is [S][64] row-major; > 0: pair-major [64][rope_ld]
   int flags;      // bit 0: EPI_STORE rounds fp32 -> fp16 -> bf16 (the reference's Triton kernel, fused_kernels.py:80)
   int n_fast;   // tile order: 0 = consecutive tiles walk down M (W tile shared, A streamed), 1 = walk along N
-  int n_group;  // n_fast only: column blocks per group (0 = all): the tile list sweeps all row bands once per group
 };
 
-// tile index -> (row block, column block) for the three tile orders
+// tile index -> (row block, column block) for the two tile orders
 __device__ __forceinline__ void tile_decode(const GemmDev& p, int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  if (!p.n_fast) {
-    m_blk = tile % num_m;
-    n_blk = tile / num_m;
-  } else if (p.n_group <= 0 || p.n_group >= num_n) {
-    m_blk = tile / num_n;
-    n_blk = tile % num_n;
-  } else {
-    const int per_group = p.n_group * num_m;          // tiles of a full group
-    const int g = tile / per_group;
-    const int n0 = g * p.n_group;
-    const int width = min(p.n_group, num_n - n0);     // the last group may be narrower
-    const int idx = tile - g * per_group;
-    m_blk = idx / width;
-    n_blk = n0 + idx % width;
-  }
+  m_blk = p.n_fast ? tile / num_n : tile % num_m;
+  n_blk = p.n_fast ? tile % num_n : tile / num_m;
 }
 
 // Tile order. A wave of concurrent tiles re-streams one operand from L2 / DRAM for every few blocks of the other
@@ -61,19 +47,9 @@ inline int pick_n_fast(const GemmArgs& a) {
   return a_bytes > 96e6 && w_bytes < a_bytes ? 1 : 0;
 }
 
-// Column blocks per group for the N-fast order (0 = no grouping, the default). Walking along N keeps one A band hot, but
-// every wave of concurrent tiles then streams the WHOLE of W, and 75 - 94 MB of W do not stay in the L2 next to the A
-// bands (ncu, FF-down 8192 x 3072 x 12288: 809 MB of DRAM reads for 277 MB of operands). Sweeping the row bands once
-// per group of column blocks whose W slice would fit was measured and REJECTED: the slice does not stay resident
-// either (781 MB, and 1 - 2 % slower, profiles/r02_n_group_l2_hints_rejected.log); pinning it with evict-last TMA
-// hints and streaming A evict-first loses the A band's reuse across the group (1011 MB, 9 % slower). These launches
-// run at 94 % tensor-pipe activity regardless. RGE_N_GROUP = n forces a group size (tests).
-inline int pick_n_group(const GemmArgs& a, int bn) {
-  (void)a; (void)bn;
-  const int forced = tuning().n_group;
-  return forced > 0 ? forced : 0;
-}
-
+// Measured and rejected (profiles/r02_n_group_l2_hints_rejected.log): sweeping the row bands once per GROUP of column
+// blocks so that a W slice stays in the L2 - it does not (781 vs 809 MB of DRAM reads for FF-down, 1-2 % slower), and
+// pinning it with evict-last TMA hints while streaming A evict-first loses the A band's reuse (1011 MB, 9 % slower).
 inline GemmDev to_dev(const GemmArgs& a) {
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
@@ -82,7 +58,6 @@ inline GemmDev to_dev(const GemmArgs& a) {
   p.norm_w = a.norm_w; p.rope_cs = a.rope_cs; p.rope_map = a.rope_map; p.rope_off = a.rope_off;
   p.rope_ld = a.rope_ld; p.flags = a.flags;
   p.n_fast = 0;
-  p.n_group = 0;
   return p;
 }
 

@@ -117,42 +117,49 @@ def test_gemm_cta_pair_kernel_tile_widths_bit_identical(bn):
         assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("M", [2304 + 77, 600])   # CTA-pair kernel, 1-CTA kernel (28 % padding to 256 rows)
-@pytest.mark.parametrize("n_group", [1, 3, 5])
-def test_gemm_grouped_n_fast_tile_order_bit_identical(M, n_group):
-    """Tile orders only permute the tile list: walking down M, along N, and along N in groups of column blocks (the order
-    K-heavy launches use so that a slice of W stays in the L2, with a narrower last group) give bit-identical results,
-    on the CTA-pair and the 1-CTA kernel."""
+@pytest.mark.parametrize("M,N,K", [(2304, 3072, 6144), (512, 3072, 12288), (2381, 1536, 6208), (4096, 3072, 15360)])
+def test_gemm_cta_pair_split_of_the_trailing_tile_wave(M, N, K):
+    """K-heavy CTA-pair launches cut the tiles of their last, partial wave along K (second launch on a side stream into
+    fp32 slabs + finish kernel that runs the same epilogue code): every epilogue that allows it, scatter, ragged M and
+    K; within bf16 rounding of the unsplit launch (the fp32 sums associate differently) and of the fp32 reference;
+    `split_tail` = 0 gives the unsplit kernel back."""
     from regione_b200 import _lib, ops
-    g = _gen(23)
-    N, K = 1792, 192
+    g = _gen(24)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).bfloat16()
     b = torch.randn(N, device="cuda", generator=g).bfloat16()
     gate = torch.randn(N, device="cuda", generator=g).bfloat16()
     res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    rows = torch.randperm(M + 100, device="cuda", generator=g)[:M].int()
 
-    def run():
+    def run_all():
+        outs = [ops.gemm(a, w, b), ops.gemm(a, w, b, epilogue=_lib.EPI_GELU)]
         o = res.clone()
         ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, gate=gate, res=o, out=o)
-        return ops.gemm(a, w, b), o
+        outs.append(o)
+        cache = torch.zeros(M + 100, N + 64, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, b, out=cache, row_map=rows, col_off=32)
+        outs.append(cache)
+        torch.cuda.synchronize()
+        return outs
 
     try:
-        ops.set_option("gemm2_bn", 256)
-        ops.set_option("gemm_bn", 128)
-        ops.set_option("raster", 0)
-        ref = run()
-        ops.set_option("raster", 1)
-        ops.set_option("n_group", 0)
-        plain = run()
-        ops.set_option("n_group", n_group)
-        got = run()
+        ops.set_option("2cta_min_m", 1)
+        ops.set_option("split_tail", 0)
+        ref = run_all()
+        ops.set_option("split_tail", 1)
+        got = run_all()
+        again = run_all()
     finally:
-        for k, v in (("raster", -1), ("n_group", -1), ("gemm2_bn", 0), ("gemm_bn", 0)):
-            ops.set_option(k, v)
-    assert rel_l2(ref[0], a.float() @ w.float().t() + b.float()) <= BF16_TOL
-    for x, y, z in zip(ref, plain, got):
-        assert torch.equal(x, y) and torch.equal(x, z)
+        ops.set_option("split_tail", 1)
+        ops.set_option("2cta_min_m", -1)
+    lin = a.float() @ w.float().t() + b.float()
+    assert rel_l2(got[0], lin) <= BF16_TOL
+    assert rel_l2(got[2], res.float() + gate.float()[None] * lin.bfloat16().float()) <= BF16_TOL
+    assert not all(torch.equal(x, y) for x, y in zip(got, ref))     # the split path did run
+    for x, y, z in zip(got, ref, again):
+        assert rel_l2(x, y) <= 2e-3                                  # differences are single bf16 roundings
+        assert torch.equal(x, z)                                     # deterministic
 
 
 @pytest.fixture
