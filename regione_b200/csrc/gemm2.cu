@@ -258,22 +258,42 @@ SplitRes* split_resources(int max_pairs) {
   return &r;
 }
 
+// Cost, in full-tile times, of the trailing `tail` tiles when each is cut into the best number of K-ranges (<= 4, each
+// at least 16 k-blocks, at most two waves of parts): ceil(tail s / pairs) / s + 0.04 s against 1 for the unsplit wave.
+double tail_cost(int tail, int pairs, int num_kb, bool allow_split, int* split) {
+  *split = 1;
+  if (tail == 0) return 0.0;
+  double best = 1.0;
+  if (allow_split && num_kb >= 96) {
+    for (int sp = 2; sp <= 4 && tail * sp <= 2 * pairs && num_kb / sp >= 16; ++sp) {
+      const double cost = (double)((tail * sp + pairs - 1) / pairs) / sp + 0.04 * sp;
+      if (cost < best - 0.15) { best = cost; *split = sp; }
+    }
+  }
+  return best;
+}
+
 // Tile width: minimise  ceil(tiles / pairs) x (bn + 60) [x 1.04 for odd multiples of 16]  over the multiples of 16 (of
 // 128 for EPI_NORM_ROPE, whose epilogue owns whole heads). The constants are fitted to the measured width sweep
 // (profiles/r02_gemm2_width_sweep.log, tools/gemm2_width_sweep.py): a narrower tile re-reads the same 128 x 64 A block
 // from shared memory for fewer FLOPs (the 256-wide tile sits exactly at the 128 B/clk the SS MMA may read), and widths
 // that are not multiples of 32 pay the 16-column epilogue tail. RGE_GEMM2_BN / "gemm2_bn" forces a width.
-int pick_bn2(const GemmArgs& a, int pairs) {
+// The K-split of the trailing wave (tail_cost) is chosen together with the width: waves = full waves + tail cost.
+int pick_bn2(const GemmArgs& a, int pairs, int* split) {
   const bool heads = a.epilogue == EPI_NORM_ROPE;
-  const int forced = tuning().gemm2_bn;
-  if (forced >= 16 && forced <= BN && forced % (heads ? 128 : 16) == 0) return forced;
+  const bool allow_split = !heads && tuning().split_tail;
+  const int num_kb = (a.K + BK - 1) / BK;
   const long num_m = (a.M + 2 * BM - 1) / (2 * BM);
-  int best = BN;
+  const int forced = tuning().gemm2_bn;
+  int best = 0;
   double best_cost = 0;
   for (int bn = BN; bn >= (heads ? 128 : 64); bn -= heads ? 128 : 16) {
+    if (forced >= 16 && forced <= BN && forced % (heads ? 128 : 16) == 0 && bn != forced) continue;
     const long tiles = num_m * ((a.N + bn - 1) / bn);
-    const double cost = (double)((tiles + pairs - 1) / pairs) * (bn + 60) * (bn % 32 ? 1.04 : 1.0);
-    if (bn == BN || cost < best_cost) { best = bn; best_cost = cost; }
+    int sp;
+    const double waves = (double)(tiles / pairs) + tail_cost((int)(tiles % pairs), pairs, num_kb, allow_split, &sp);
+    const double cost = waves * (bn + 60) * (bn % 32 ? 1.04 : 1.0);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; *split = sp; }
   }
   return best;
 }
@@ -288,7 +308,8 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     attr_set[dev] = true;
   }
   const int max_pairs = num_sms / 2;
-  const int bn = pick_bn2(a, max_pairs);
+  int split = 1;
+  const int bn = pick_bn2(a, max_pairs, &split);
   CUtensorMap map_a, map_b;
   if (!make_tmap_bf16_2d(&map_a, a.A, a.M, a.K, a.lda, BM)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_2d(&map_b, a.W, a.N, a.K, a.ldw, bn / 2)) return cudaErrorInvalidValue;
@@ -296,16 +317,7 @@ cudaError_t launch_t(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   p.n_fast = pick_n_fast(a);
   const int num_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + bn - 1) / bn);
   const int num_kb = (a.K + BK - 1) / BK;
-  // split of the trailing partial wave along K (see SplitRes)
-  int split = 1;
   const int tail = num_tiles % max_pairs;
-  if (EPI != EPI_NORM_ROPE && tuning().split_tail && num_kb >= 96 && tail > 0) {
-    double best = 0.85;
-    for (int sp = 2; sp <= 4 && tail * sp <= 2 * max_pairs && num_kb / sp >= 16; ++sp) {
-      const double cost = (double)((tail * sp + max_pairs - 1) / max_pairs) / sp + 0.04 * sp;
-      if (cost < best) { best = cost; split = sp; }
-    }
-  }
   SplitRes* res = split > 1 ? split_resources(max_pairs) : nullptr;
   if (!res) {
     const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
