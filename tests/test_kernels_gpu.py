@@ -117,51 +117,6 @@ def test_gemm_cta_pair_kernel_tile_widths_bit_identical(bn):
         assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("M,N,K", [(2304, 3072, 6144), (512, 3072, 12288), (2381, 1536, 6208), (4096, 3072, 15360)])
-def test_gemm_cta_pair_split_of_the_trailing_tile_wave(M, N, K):
-    """K-heavy CTA-pair launches cut the tiles of their last, partial wave along K (second launch on a side stream into
-    fp32 slabs + finish kernel that runs the same epilogue code): every epilogue that allows it, scatter, ragged M and
-    K; within bf16 rounding of the unsplit launch (the fp32 sums associate differently) and of the fp32 reference;
-    `split_tail` = 0 gives the unsplit kernel back."""
-    from regione_b200 import _lib, ops
-    g = _gen(24)
-    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).bfloat16()
-    b = torch.randn(N, device="cuda", generator=g).bfloat16()
-    gate = torch.randn(N, device="cuda", generator=g).bfloat16()
-    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
-    rows = torch.randperm(M + 100, device="cuda", generator=g)[:M].int()
-
-    def run_all():
-        outs = [ops.gemm(a, w, b), ops.gemm(a, w, b, epilogue=_lib.EPI_GELU)]
-        o = res.clone()
-        ops.gemm(a, w, b, epilogue=_lib.EPI_GATE_RES, gate=gate, res=o, out=o)
-        outs.append(o)
-        cache = torch.zeros(M + 100, N + 64, device="cuda", dtype=torch.bfloat16)
-        ops.gemm(a, w, b, out=cache, row_map=rows, col_off=32)
-        outs.append(cache)
-        torch.cuda.synchronize()
-        return outs
-
-    try:
-        ops.set_option("2cta_min_m", 1)
-        ops.set_option("split_tail", 0)
-        ref = run_all()
-        ops.set_option("split_tail", 1)
-        got = run_all()
-        again = run_all()
-    finally:
-        ops.set_option("split_tail", 1)
-        ops.set_option("2cta_min_m", -1)
-    lin = a.float() @ w.float().t() + b.float()
-    assert rel_l2(got[0], lin) <= BF16_TOL
-    assert rel_l2(got[2], res.float() + gate.float()[None] * lin.bfloat16().float()) <= BF16_TOL
-    assert not all(torch.equal(x, y) for x, y in zip(got, ref))     # the split path did run
-    for x, y, z in zip(got, ref, again):
-        assert rel_l2(x, y) <= 2e-3                                  # differences are single bf16 roundings
-        assert torch.equal(x, z)                                     # deterministic
-
-
 @pytest.fixture
 def one_cta_kernel():
     """Keeps every launch on the 1-CTA kernel (the per-shape rule would send well-filled REGION sizes to the CTA pair)."""
