@@ -1027,9 +1027,7 @@ static int dit_step_impl(rge_handle* h, int32_t pass, const void* x_in, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   NvtxRange step_range(sel ? "rge_dit_step REGION (%d active image tokens, pass %d)"
                            : "rge_dit_step FULL (%d image tokens, pass %d)", n_img, pass);
-  const int D = h->D, T = h->Tp[pass], Dm = h->Dm, S = T + h->L + h->C, M = n_img, MA = T + n_img;
-  const long ldb = D + Dm;  // `big`: attention output in columns [0,D), MLP hidden in [D, D+Dm)
-  const float2* rope = h->rope + (size_t)pass * h->S * 64;
+  const int D = h->D, T = h->Tp[pass], M = n_img, MA = T + n_img;
   bf16* tproj = h->small;
   bf16* t2 = tproj + 256 + D;
   bf16* temb = t2 + D;
