@@ -24,7 +24,8 @@ struct GemmDev {
   const int* rope_map;
   int rope_off;
   long rope_ld;   // 0: rope_cs is [S][64] row-major; > 0: pair-major [64][rope_ld]
-  int flags;      // bit 0: EPI_STORE rounds fp32 -> fp16 -> bf16 (the reference's Triton kernel, fused_kernels.py:80)
+  int flags;      // bit 0: EPI_STORE rounds fp32 -> fp16 -> bf16 (the reference's Triton kernel, fused_kernels.py:80);
+                  // bit 1 (set by to_dev): output rows are 32-byte aligned, the epilogues use 256-bit stores
   int n_fast;   // tile order: 0 = consecutive tiles walk down M (W tile shared, A streamed), 1 = walk along N
 };
 
@@ -56,7 +57,11 @@ inline GemmDev to_dev(const GemmArgs& a) {
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.row_map = a.row_map; p.row_off = a.row_off; p.col_off = a.col_off;
   p.gate = a.gate; p.res = a.res; p.ldr = a.ldr;
   p.norm_w = a.norm_w; p.rope_cs = a.rope_cs; p.rope_map = a.rope_map; p.rope_off = a.rope_off;
-  p.rope_ld = a.rope_ld; p.flags = a.flags;
+  p.rope_ld = a.rope_ld;
+  // bit 1: every output row segment the epilogues store starts 32-byte aligned -> 256-bit stores
+  const bool wide = tuning().wide_store && (reinterpret_cast<uintptr_t>(a.out) % 32 == 0) && (a.ldo % 16 == 0) &&
+                    (a.col_off % 16 == 0);
+  p.flags = (a.flags & 1) | (wide ? 2 : 0);
   p.n_fast = 0;
   return p;
 }
@@ -71,6 +76,24 @@ __device__ __forceinline__ void ld_vec8(const __nv_bfloat16* ptr, float (&f)[8])
   for (int i = 0; i < 4; ++i) {
     f[2 * i] = __uint_as_float(w[i] << 16);
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// NW 32-bit words of one output row: 256-bit stores (STG.256, one full 32-byte sector per instruction) when the row is
+// 32-byte aligned (GemmDev::flags bit 1, checked on the host), 128-bit stores otherwise. NW is a multiple of 4.
+template <int NW>
+__device__ __forceinline__ void store_row_words(__nv_bfloat16* dst, const uint32_t* o, bool wide) {
+  if (wide && NW % 8 == 0) {
+#pragma unroll
+    for (int t = 0; t < NW / 8; ++t)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * t), "r"(o[8 * t]),
+                   "r"(o[8 * t + 1]), "r"(o[8 * t + 2]), "r"(o[8 * t + 3]), "r"(o[8 * t + 4]), "r"(o[8 * t + 5]),
+                   "r"(o[8 * t + 6]), "r"(o[8 * t + 7])
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int t = 0; t < NW / 4; ++t)
+      reinterpret_cast<uint4*>(dst)[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
   }
 }
 
@@ -112,11 +135,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
       o[4 * g + (j >> 1)] = pack_bf16x2(x0, x1);
     }
   }
-  if (valid) {
-    uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0);
-#pragma unroll
-    for (int t = 0; t < NG; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-  }
+  if (valid) store_row_words<4 * NG>(out_ptr + n0, o, (p.flags & 2) != 0);
 }
 
 template <int EPI, int NG = 4>
@@ -220,11 +239,7 @@ __device__ __forceinline__ void norm_rope_heads(const GemmDev& p, uint32_t taddr
           o[4 * g + j] = pack_bf16x2(x0 * t.x - x1 * t.y, x1 * t.x + x0 * t.y);
         }
       }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(out_ptr + n0 + h * 128 + c * 32);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
-      }
+      if (valid) store_row_words<16>(out_ptr + n0 + h * 128 + c * 32, o, (p.flags & 2) != 0);
     }
     if (c < 3) {
 #pragma unroll

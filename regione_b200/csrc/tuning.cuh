@@ -24,6 +24,7 @@ struct Tuning {
   int gemm2_bn;      // RGE_GEMM2_BN:    forced tile width of the CTA-pair GEMM (multiple of 16), 0 = choose per launch
   int min_m_2cta;    // RGE_2CTA_MIN_M:  rows from which the CTA-pair GEMM is used, 0 = never, -1 = per-shape rule (default)
   int raster;        // RGE_RASTER:      -1 = choose per launch, 0 = walk down M, 1 = walk along N
+  int wide_store;    // RGE_WIDE_STORE:  1 = 256-bit global stores in the GEMM epilogues where rows are 32-byte aligned
   int trim_last;     // RGE_TRIM_LAST:   1 = the last block computes only the rows whose output is kept (default)
   int split_mod;     // RGE_SPLIT_MOD:   1 = modulation GEMV of all but the first blocks on a side stream (default)
   int nvtx;          // RGE_NVTX:        1 = NVTX ranges per step / block / stage (profilers only)
@@ -45,6 +46,7 @@ inline Tuning& tuning() {
     x.min_m_2cta = env_int("RGE_2CTA_MIN_M", -1);
     const char* r = getenv("RGE_RASTER");
     x.raster = !r ? -1 : (r[0] == 'n' ? 1 : (r[0] == 'm' ? 0 : -1));
+    x.wide_store = env_int("RGE_WIDE_STORE", 1);
     x.trim_last = env_int("RGE_TRIM_LAST", 1);
     x.split_mod = env_int("RGE_SPLIT_MOD", 1);
     x.nvtx = env_int("RGE_NVTX", 0);
@@ -63,6 +65,7 @@ inline bool set_tuning(const char* name, int value) {
   else if (!strcmp(name, "gemm2_bn")) t.gemm2_bn = value;
   else if (!strcmp(name, "2cta_min_m")) t.min_m_2cta = value;
   else if (!strcmp(name, "raster")) t.raster = value;
+  else if (!strcmp(name, "wide_store")) t.wide_store = value;
   else if (!strcmp(name, "trim_last")) t.trim_last = value;
   else if (!strcmp(name, "split_mod")) t.split_mod = value;
   else if (!strcmp(name, "nvtx")) t.nvtx = value;
