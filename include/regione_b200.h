@@ -33,7 +33,7 @@ enum rge_status {
 int rge_abi_version(void);
 const char* rge_last_error(void);
 /* Run-time tuning knob of the kernels (same names as the RGE_* environment variables they start from, lower case
- * without the prefix: "attn_kernel", "attn_poly", "attn_split", "gemm_bn", "gemm2_bn", "2cta_min_m", "raster", "trim_last", "nvtx"). For
+ * without the prefix: "attn_kernel", "attn_poly", "attn_split", "gemm_bn", "gemm2_bn", "2cta_min_m", "raster", "wide_store", "trim_last", "nvtx"). For
  * benchmarks that sweep variants inside one process; results never depend on them beyond the stated tolerances. */
 int rge_set_option(const char* name, int32_t value);
 

@@ -61,7 +61,7 @@ def gemm_group(members):
 
 def set_option(name: str, value: int) -> None:
     """Run-time tuning knob of the kernels (rge_set_option): "attn_kernel", "attn_poly", "attn_split", "gemm_bn", "gemm2_bn", "2cta_min_m",
-    "raster", "trim_last", "nvtx"."""
+    "raster", "wide_store", "trim_last", "nvtx"."""
     check(_lib.load().rge_set_option(name.encode(), int(value)), f"rge_set_option({name})")
 
 
