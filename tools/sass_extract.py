@@ -35,6 +35,7 @@ def main():
                 "tensor paths (must be 0)\n")
         for k, lines in kernels.items():
             ops = collections.Counter()
+            stg256 = sum(1 for ln in lines if re.search(r"\bSTG\.[A-Z0-9.]*256\b", ln))
             for ln in lines:
                 body = ln.split("*/", 1)[1] if "*/" in ln else ln
                 mm = re.search(r"\b([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_]+)*)", body.replace("@P", " ").replace("@!P", " "))
@@ -49,8 +50,8 @@ def main():
                 continue
             short = k.split("(")[0]
             f.write(f"{short}: {len(lines)} instructions; " + ", ".join(f"{w} {ops[w]}" for w in WATCH if ops[w]) +
-                    f"; HMMA {ops['HMMA']}, HGMMA {ops['HGMMA']}\n")
-            if any(t in short for t in ("attention_kernel<2>", "attention_kernel<0>", "gemm2_kernel<3>", "gemm2_kernel<2>",
+                    (f", STG.256 {stg256}" if stg256 else "") + f"; HMMA {ops['HMMA']}, HGMMA {ops['HGMMA']}\n")
+            if any(t in short for t in ("attention_kernel<3>", "attention_kernel<0>", "gemm2_kernel<3>", "gemm2_kernel<2>",
                                         "gemm_kernel<0>")):
                 fn = re.sub(r"[^A-Za-z0-9]+", "_", short).strip("_")
                 with open(os.path.join(out_dir, f"{prefix}_sass_{fn}.txt"), "w") as g:
